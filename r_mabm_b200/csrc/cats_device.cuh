@@ -1,0 +1,303 @@
+// cats_device.cuh -- device-side primitives of the CATS period kernel:
+// deterministic math, Philox-4x32-10, draw sources (Philox or replay tape), warp reductions,
+// TMA bulk-copy / mbarrier wrappers.  Everything here implements docs/MODEL.md sections 3-4.
+//
+// Build note: this translation unit is compiled with -fmad=false.  The spec's arithmetic is
+// "every * and + rounds separately", which is what makes the kernels bit-exact against the CPU
+// oracle (gcc -ffp-contract=off).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cats_layout.h"
+
+namespace cats {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// draw phases (Philox counter word 1 = phase << 8 | block) and market ids
+enum { PH_PRICE_C = 1, PH_PRICE_K = 2, PH_INVEST = 3, PH_FIRE = 4, PH_JOB = 5, PH_CAP = 6,
+       PH_GOODS = 7, PH_ORDER = 8 };
+enum { MKT_JOB = 0, MKT_CAP = 1, MKT_GOODS = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// deterministic exp / log  (docs/MODEL.md section 4)
+__device__ __forceinline__ double det_exp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.0) return __longlong_as_double(0x7ff0000000000000LL);
+    if (x < -708.0) return 0.0;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double INV_LN2 = 1.44269504088896338700e+00;
+    double kf = floor(x * INV_LN2 + 0.5);
+    double r = (x - kf * LN2_HI) - kf * LN2_LO;
+    double p = 1.0 / 6227020800.0;
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    long long ki = (long long)kf;
+    double scale = __longlong_as_double((ki + 1023) << 52);
+    return p * scale;
+}
+
+__device__ __forceinline__ double det_log(double x)
+{
+    if (x != x) return x;
+    if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+    if (x == 0.0) return __longlong_as_double(0xfff0000000000000LL);
+    if (x == __longlong_as_double(0x7ff0000000000000LL)) return x;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    long long e = (long long)((b >> 52) & 0x7ff);
+    if (e == 0) {
+        x = x * 18014398509481984.0;
+        b = (unsigned long long)__double_as_longlong(x);
+        e = (long long)((b >> 52) & 0x7ff) - 54;
+    }
+    e -= 1023;
+    double m = __longlong_as_double((long long)((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double z = s * s;
+    double p = 1.0 / 23.0;
+    p = p * z + 1.0 / 21.0;
+    p = p * z + 1.0 / 19.0;
+    p = p * z + 1.0 / 17.0;
+    p = p * z + 1.0 / 15.0;
+    p = p * z + 1.0 / 13.0;
+    p = p * z + 1.0 / 11.0;
+    p = p * z + 1.0 / 9.0;
+    p = p * z + 1.0 / 7.0;
+    p = p * z + 1.0 / 5.0;
+    p = p * z + 1.0 / 3.0;
+    p = p * z;
+    double lm = 2.0 * (s + s * p);
+    double ef = (double)e;
+    return ef * LN2_HI + (lm + ef * LN2_LO);
+}
+
+// ---------------------------------------------------------------------------------------------
+// det_sum: lane l adds x[l], x[l+32], ... in order, then an xor butterfly 16,8,4,2,1.
+// Must be called by all 32 lanes of a warp; every lane gets the result.
+template <class Fn>
+__device__ __forceinline__ double warp_det_sum(int n, int lane, Fn val)
+{
+    double a = 0.0;
+    for (int i = lane; i < n; i += 32) a = a + val(i);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a = a + __shfl_xor_sync(FULL, a, off);
+    return a;
+}
+
+template <class Fn>
+__device__ __forceinline__ int warp_int_sum(int n, int lane, Fn val)
+{
+    int a = 0;
+    for (int i = lane; i < n; i += 32) a += val(i);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(FULL, a, off);
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox-4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
+{
+    unsigned long long m = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
+    return (double)m * (1.0 / 9007199254740992.0);
+}
+
+// the draw source of one economy-period
+struct Draws {
+    const unsigned char *tape;  // nullptr => Philox
+    uint32_t k0, k1, period, economy;
+    TapeOff t;
+    int z_c, z_k, z_e;
+
+    __device__ __forceinline__ uint4 philox(uint32_t agent, uint32_t phase, uint32_t block) const
+    {
+        return philox4x32_10(agent, (phase << 8) | block, period, economy, k0, k1);
+    }
+    __device__ __forceinline__ double uniform(uint32_t phase, int agent) const
+    {
+        if (tape) {
+            uint32_t off = phase == PH_PRICE_C ? t.u_price_c : phase == PH_PRICE_K ? t.u_price_k : t.u_invest;
+            return *reinterpret_cast<const double *>(tape + off + 8u * (uint32_t)agent);
+        }
+        uint4 w = philox((uint32_t)agent, phase, 0);
+        return u01(w.x, w.y);
+    }
+    __device__ __forceinline__ uint32_t fire_key(int worker) const
+    {
+        if (tape) return *reinterpret_cast<const uint32_t *>(tape + t.fire_key + 4u * (uint32_t)worker);
+        return philox((uint32_t)worker, PH_FIRE, 0).x;
+    }
+    // z distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
+    __device__ __forceinline__ void candidates(uint32_t phase, int agent, int n, int z, int (&out)[MAX_Z]) const
+    {
+        if (tape) {
+            uint32_t off; int zz;
+            if (phase == PH_JOB) { off = t.job_cand; zz = z_e; }
+            else if (phase == PH_CAP) { off = t.cap_cand; zz = z_k; }
+            else { off = t.goods_cand; zz = z_c; }
+            const int *src = reinterpret_cast<const int *>(tape + off) + (size_t)agent * (size_t)zz;
+#pragma unroll
+            for (int k = 0; k < MAX_Z; ++k) out[k] = k < z ? src[k] : 0;
+            return;
+        }
+        uint32_t w[MAX_Z];
+        uint4 a = philox((uint32_t)agent, phase, 0);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = w[5] = w[6] = w[7] = 0;
+        if (z > 4) {
+            uint4 b = philox((uint32_t)agent, phase, 1);
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        }
+        int jpos[MAX_Z], jval[MAX_Z];
+#pragma unroll
+        for (int k = 0; k < MAX_Z; ++k) {
+            out[k] = 0; jpos[k] = -1; jval[k] = 0;
+            if (k < z) {
+                int j = k + (int)__umulhi(w[k], (uint32_t)(n - k));
+                int v = j, vk = k;
+#pragma unroll
+                for (int q = 0; q < k; ++q) {
+                    if (jpos[q] == j) v = jval[q];
+                    if (jpos[q] == k) vk = jval[q];
+                }
+                out[k] = v; jpos[k] = j; jval[k] = vk;
+            }
+        }
+    }
+};
+
+// visiting order of a market: tape permutation, or the keyed bijection of docs/MODEL.md 3.3
+struct Order {
+    const int *tape_order;
+    uint32_t m0, m1, m2, m3, a0, a1, a2, a3, mask;
+    int s, n;
+    __device__ __forceinline__ void init(const Draws &d, int market, int n_)
+    {
+        n = n_; tape_order = nullptr;
+        if (d.tape) {
+            uint32_t off = market == MKT_JOB ? d.t.job_order : market == MKT_CAP ? d.t.cap_order : d.t.goods_order;
+            tape_order = reinterpret_cast<const int *>(d.tape + off);
+            return;
+        }
+        uint4 w0 = d.philox((uint32_t)market, PH_ORDER, 0), w1 = d.philox((uint32_t)market, PH_ORDER, 1);
+        int b = 1;
+        while ((1u << b) < (uint32_t)n) ++b;
+        mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+        s = b / 2 > 0 ? b / 2 : 1;
+        m0 = w0.x | 1u; m1 = w0.y | 1u; m2 = w1.x | 1u; m3 = w1.y | 1u;
+        a0 = w0.z; a1 = w0.w; a2 = w1.z; a3 = w1.w;
+    }
+    __device__ __forceinline__ int at(int pos) const
+    {
+        if (tape_order) return tape_order[pos];
+        uint32_t x = (uint32_t)pos;
+        do {
+            x = (x * m0 + a0) & mask; x ^= x >> s;
+            x = (x * m1 + a1) & mask; x ^= x >> s;
+            x = (x * m2 + a2) & mask; x ^= x >> s;
+            x = (x * m3 + a3) & mask; x ^= x >> s;
+        } while (x >= (uint32_t)n);
+        return (int)x;
+    }
+};
+
+// stable ascending sort of up to MAX_Z (candidate, price) pairs, register only (rank sort)
+__device__ __forceinline__ void sort_by_price(int (&cand)[MAX_Z], double (&pr)[MAX_Z], int z)
+{
+    int rank[MAX_Z];
+#pragma unroll
+    for (int a = 0; a < MAX_Z; ++a) {
+        rank[a] = 0;
+#pragma unroll
+        for (int b = 0; b < MAX_Z; ++b)
+            if (a < z && b < z && b != a)
+                rank[a] += (pr[b] < pr[a] || (pr[b] == pr[a] && b < a)) ? 1 : 0;
+    }
+    int sc[MAX_Z]; double sp[MAX_Z];
+#pragma unroll
+    for (int r = 0; r < MAX_Z; ++r) {
+        sc[r] = cand[r]; sp[r] = pr[r];
+#pragma unroll
+        for (int a = 0; a < MAX_Z; ++a)
+            if (a < z && rank[a] == r) { sc[r] = cand[a]; sp[r] = pr[a]; }
+    }
+#pragma unroll
+    for (int r = 0; r < MAX_Z; ++r) { cand[r] = sc[r]; pr[r] = sp[r]; }
+}
+
+__device__ __forceinline__ int d2count(double x)
+{
+    if (!(x > 0.0)) return 0;
+    if (x > 1.0e9) return 1000000000;
+    return (int)x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace cats

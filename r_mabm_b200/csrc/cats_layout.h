@@ -1,0 +1,114 @@
+// cats_layout.h -- economy blob / on-chip working-set layout shared by host and device code.
+//
+// One economy = one contiguous blob in HBM (docs/MODEL.md section 2, docs/DESIGN.md "data layout").
+// The shared-memory working set of the period kernel starts with a byte-identical image of the
+// blob (so the HBM<->smem transfer is a single bulk copy) followed by the transients that live
+// inside one period only.  All section offsets are multiples of 16 bytes (bulk-copy granularity).
+#pragma once
+#include <stdint.h>
+
+namespace cats {
+
+constexpr int NC_FIELDS = 16;
+constexpr int NK_FIELDS = 14;
+constexpr int N_SCAL = 32;
+constexpr int N_PARAMS = 34;
+constexpr int N_STATS = 16;
+constexpr int MAX_Z = 8;
+
+// parameter slots: Cats._default_parameters key order (/root/reference/rmabm/environments/cats.py:69-104)
+enum {
+    P_z_c, P_z_k, P_z_e, P_xi, P_chi, P_q_adj, P_p_adj, P_mu, P_eta, P_Iprob, P_phi, P_theta,
+    P_delta, P_alpha, P_k, P_div, P_barX, P_inventory_depreciation, P_b1, P_b2, P_b_k1, P_b_k2,
+    P_interest_rate, P_subsidy, P_maastricht, P_target_deficit, P_tax_rate, P_wage_update_up,
+    P_wage_update_down, P_u_target, P_wb, P_tax_rate_d, P_r_f, P_E_threshold_scale,
+    // derived, filled on chip
+    P_log1mtheta = 34, P_SLOTS = 40
+};
+
+// scalar slots of the blob (model.agg / bank / gov of the reference, cats.py:567-607)
+enum {
+    S_timestep, S_price, S_price_k, S_init_price, S_init_price_k, S_wb, S_Y_real, S_Y_nominal_tot,
+    S_gdp_deflator, S_inflationRate, S_Un, S_consumption, S_totK, S_bankruptcy_rate,
+    S_bank_E, S_bank_loans, S_profitsB, S_dividendsB, S_bank_interest_income, S_bank_bad_debt,
+    S_gov_bonds, S_GB, S_deficitGDP, S_gov_TA, S_gov_G, S_gov_r_b, S_gov_subsidy_level,
+    S_terminated, S_status, S_reserved0, S_reserved1, S_reserved2
+};
+
+// C-firm / K-firm float64 rows
+enum { C_De, C_P, C_Y_prev, C_Yd, C_Q, C_A, C_K, C_investment, C_capital_value, C_wages,
+       C_interests, C_deb, C_liquidity, C_barYK, C_interest_r, C_div_income };
+enum { K_De, K_P, K_Y_prev, K_Yd, K_Q, K_A, K_wages, K_interests, K_deb, K_liquidity,
+       K_interest_r, K_div_income, K_inv, K_Yavail };
+
+struct Layout {
+    int32_t W, F, N, H;
+    int32_t rowF, rowN;  // bytes of one firm f64 row
+    // persisted sections (byte offsets inside the blob)
+    int32_t o_scal, o_c, o_k, o_Leff, o_PA, o_perm, o_Oc, blob;
+    // transients (byte offsets inside the working set; all >= blob)
+    int32_t o_Ld, o_vac, o_cFtot, o_cKdem, o_cYstock, o_cvalinv, o_kFtot, o_kYstock, o_budget,
+        workset;
+    // scratch that is never dumped
+    int32_t o_seekers, o_bad, o_red, o_par, o_misc, smem;
+};
+
+__host__ __device__ inline int32_t up16(int64_t x) { return (int32_t)((x + 15) & ~(int64_t)15); }
+
+inline Layout make_layout(int W, int F, int N)
+{
+    Layout L;
+    L.W = W; L.F = F; L.N = N; L.H = W + F + N;
+    L.rowF = up16(8ll * F); L.rowN = up16(8ll * N);
+    int64_t o = 0;
+    L.o_scal = (int32_t)o; o += 8 * N_SCAL;
+    L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
+    L.o_k = (int32_t)o; o += (int64_t)NK_FIELDS * L.rowN;
+    L.o_Leff = (int32_t)o; o += up16(4ll * (F + N));
+    L.o_PA = (int32_t)o; o += up16(8ll * L.H);
+    L.o_perm = (int32_t)o; o += up16(8ll * L.H);
+    L.o_Oc = (int32_t)o; o += up16(4ll * W);
+    o = (o + 127) & ~(int64_t)127;
+    L.blob = (int32_t)o;
+    L.o_Ld = (int32_t)o; o += up16(4ll * (F + N));
+    L.o_vac = (int32_t)o; o += up16(4ll * (F + N));
+    L.o_cFtot = (int32_t)o; o += L.rowF;
+    L.o_cKdem = (int32_t)o; o += L.rowF;
+    L.o_cYstock = (int32_t)o; o += L.rowF;
+    L.o_cvalinv = (int32_t)o; o += L.rowF;
+    L.o_kFtot = (int32_t)o; o += L.rowN;
+    L.o_kYstock = (int32_t)o; o += L.rowN;
+    L.o_budget = (int32_t)o; o += up16(8ll * L.H);
+    L.workset = (int32_t)o;
+    L.o_seekers = (int32_t)o; o += up16(4ll * W);
+    L.o_bad = (int32_t)o; o += up16(F + N);
+    L.o_red = (int32_t)o; o += 8 * 64;
+    L.o_par = (int32_t)o; o += 8 * P_SLOTS;
+    L.o_misc = (int32_t)o; o += 256;
+    L.smem = (int32_t)o;
+    return L;
+}
+
+struct TapeOff {
+    uint32_t u_price_c, u_price_k, u_invest, fire_key, job_order, job_cand, cap_order, cap_cand,
+        goods_order, goods_cand, bytes;
+};
+
+inline TapeOff make_tape(int W, int F, int N, int z_c, int z_k, int z_e)
+{
+    TapeOff t; uint64_t o = 0; uint64_t H = (uint64_t)W + F + N;
+    t.u_price_c = (uint32_t)o; o += 8ull * F;
+    t.u_price_k = (uint32_t)o; o += 8ull * N;
+    t.u_invest = (uint32_t)o; o += 8ull * F;
+    t.fire_key = (uint32_t)o; o += 4ull * W;
+    t.job_order = (uint32_t)o; o += 4ull * W;
+    t.job_cand = (uint32_t)o; o += 4ull * W * z_e;
+    t.cap_order = (uint32_t)o; o += 4ull * F;
+    t.cap_cand = (uint32_t)o; o += 4ull * F * z_k;
+    t.goods_order = (uint32_t)o; o += 4ull * H;
+    t.goods_cand = (uint32_t)o; o += 4ull * H * z_c;
+    t.bytes = (uint32_t)((o + 15) & ~15ull);
+    return t;
+}
+
+}  // namespace cats

@@ -111,6 +111,8 @@ typedef struct cats_step_args {
     double *d_stats;            /* out [B][n_periods][CATS_N_STATS] or NULL */
     const uint8_t *d_tape;      /* replay: [B][n_periods] records of cats_tape_bytes(); NULL = Philox */
     int32_t tape_z[3];          /* z_c, z_k, z_e the tape records were laid out with (only read when d_tape != NULL) */
+    int32_t max_z;              /* upper bound on z_c, z_k, z_e over all economies of the call (1..8);
+                                   0 = unknown (8).  <= 5 selects the leaner kernel instantiation. */
     int32_t stop_phase;         /* debug: halt the (single) period after this phase id; 0 = off */
     void *d_debug;              /* debug: [B][cats_workset_bytes] image of the on-chip working set */
     void *stream;
@@ -129,7 +131,7 @@ int cats_step_host(const cats_step_args *args_with_host_io, void *d_scratch);
 /* Size of the on-chip working set image written to d_debug (blob + transients). */
 size_t cats_workset_bytes(int W, int F, int N);
 /* Describe a transient field inside the working-set image (same contract as cats_field_info).
- * Names: c_Ld c_vac k_Ld k_vac (i32), c_Ftot c_Kdem c_Ystock c_valinv k_Ftot k_Ystock budget (f64). */
+ * Names: c_Ld c_vac k_Ld k_vac (i32), c_Ftot c_Kdem c_Ystock c_valinv k_Ftot k_Ystock (f64). */
 int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset,
                             int32_t *count, int32_t *dtype);
 
@@ -140,6 +142,12 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t cats_launch_count(void);
+
+/* Debug/profiling aid: when set to a device array of 16 int64, block 0 of every later cats_step
+ * adds its clock64() cycles per phase group into it (slots: 0 firm decisions, 1 fire, 2 job search,
+ * 3 produce, 4 capital market, 5 income+budget, 6 goods market, 7 accounting, 8 reward, 9 tracking,
+ * 10 bankruptcy, 11 closing).  Pass NULL to switch it off. */
+void cats_debug_phase_cycles(void *d_cycles16);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
     "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
-    "cats_launch_count",
+    "cats_launch_count", "cats_debug_phase_cycles",
 ]
 
 
@@ -43,7 +43,7 @@ class StepArgs(C.Structure):
         ("d_action_mask", C.c_void_p), ("bankruptcy_reward", C.c_double), ("d_obs", C.c_void_p),
         ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p), ("d_status", C.c_void_p),
         ("d_stats", C.c_void_p), ("d_tape", C.c_void_p), ("tape_z", C.c_int32 * 3),
-        ("stop_phase", C.c_int32), ("d_debug", C.c_void_p), ("stream", C.c_void_p),
+        ("max_z", C.c_int32), ("stop_phase", C.c_int32), ("d_debug", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     L.cats_step_host.argtypes = [C.POINTER(StepArgs), C.c_void_p]
     L.cats_launch_info.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int32)] * 4
     L.cats_launch_count.restype = C.c_uint64
+    L.cats_debug_phase_cycles.argtypes = [C.c_void_p]
+    L.cats_debug_phase_cycles.restype = None
     if L.cats_abi_version() != 1:
         raise ImportError(f"{LIB_PATH}: ABI version {L.cats_abi_version()} != 1; rebuild")
     _lib = L

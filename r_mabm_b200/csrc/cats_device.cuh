@@ -158,7 +158,8 @@ struct Draws {
         return philox((uint32_t)worker, PH_FIRE, 0).x;
     }
     // z distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
-    __device__ __forceinline__ void candidates(uint32_t phase, int agent, int n, int z, int (&out)[MAX_Z]) const
+    template <int ZM>
+    __device__ __forceinline__ void candidates(uint32_t phase, int agent, int n, int z, int (&out)[ZM]) const
     {
         if (tape) {
             uint32_t off; int zz;
@@ -167,20 +168,20 @@ struct Draws {
             else { off = t.goods_cand; zz = z_c; }
             const int *src = reinterpret_cast<const int *>(tape + off) + (size_t)agent * (size_t)zz;
 #pragma unroll
-            for (int k = 0; k < MAX_Z; ++k) out[k] = k < z ? src[k] : 0;
+            for (int k = 0; k < ZM; ++k) out[k] = k < z ? src[k] : 0;
             return;
         }
-        uint32_t w[MAX_Z];
+        uint32_t w[8];
         uint4 a = philox((uint32_t)agent, phase, 0);
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
         w[4] = w[5] = w[6] = w[7] = 0;
-        if (z > 4) {
+        if (ZM > 4 && z > 4) {
             uint4 b = philox((uint32_t)agent, phase, 1);
             w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         }
-        int jpos[MAX_Z], jval[MAX_Z];
+        int jpos[ZM], jval[ZM];
 #pragma unroll
-        for (int k = 0; k < MAX_Z; ++k) {
+        for (int k = 0; k < ZM; ++k) {
             out[k] = 0; jpos[k] = -1; jval[k] = 0;
             if (k < z) {
                 int j = k + (int)__umulhi(w[k], (uint32_t)(n - k));
@@ -232,27 +233,28 @@ struct Order {
 };
 
 // stable ascending sort of up to MAX_Z (candidate, price) pairs, register only (rank sort)
-__device__ __forceinline__ void sort_by_price(int (&cand)[MAX_Z], double (&pr)[MAX_Z], int z)
+template <int ZM>
+__device__ __forceinline__ void sort_by_price(int (&cand)[ZM], double (&pr)[ZM], int z)
 {
-    int rank[MAX_Z];
+    int rank[ZM];
 #pragma unroll
-    for (int a = 0; a < MAX_Z; ++a) {
+    for (int a = 0; a < ZM; ++a) {
         rank[a] = 0;
 #pragma unroll
-        for (int b = 0; b < MAX_Z; ++b)
+        for (int b = 0; b < ZM; ++b)
             if (a < z && b < z && b != a)
                 rank[a] += (pr[b] < pr[a] || (pr[b] == pr[a] && b < a)) ? 1 : 0;
     }
-    int sc[MAX_Z]; double sp[MAX_Z];
+    int sc[ZM]; double sp[ZM];
 #pragma unroll
-    for (int r = 0; r < MAX_Z; ++r) {
+    for (int r = 0; r < ZM; ++r) {
         sc[r] = cand[r]; sp[r] = pr[r];
 #pragma unroll
-        for (int a = 0; a < MAX_Z; ++a)
+        for (int a = 0; a < ZM; ++a)
             if (a < z && rank[a] == r) { sc[r] = cand[a]; sp[r] = pr[a]; }
     }
 #pragma unroll
-    for (int r = 0; r < MAX_Z; ++r) { cand[r] = sc[r]; pr[r] = sp[r]; }
+    for (int r = 0; r < ZM; ++r) { cand[r] = sc[r]; pr[r] = sp[r]; }
 }
 
 __device__ __forceinline__ int d2count(double x)
@@ -270,6 +272,11 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

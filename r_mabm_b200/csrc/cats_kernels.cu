@@ -47,6 +47,7 @@ struct KArgs {
     const unsigned char *tape;
     int stop_phase;
     unsigned char *debug;
+    long long *cycles;  // debug: [16] per-phase clock64 totals of block 0
 };
 
 // per-block view of the shared-memory working set
@@ -55,12 +56,14 @@ struct Ctx {
     const KArgs *a;
     double *scal, *par;
     int *Leff, *Ld, *vac, *Oc;
-    double *PA, *perm, *budget, *red;
+    double *PA, *perm;  // household tail: GLOBAL memory (blob), not shared
+    double *red;
     int *misc;
     unsigned char *bad;
     int tid, lane, warp, nwarps, nt;
     long long b;  // economy index inside this launch
     int last;     // last phase id to execute (stop_phase or 99)
+    unsigned par_full, par_empty;  // mbarrier phase parities of the goods-market ring (bit s = slot s)
     Draws d;
     __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_c + field * a->L.rowF); }
     __device__ __forceinline__ double *kf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_k + field * a->L.rowN); }
@@ -68,7 +71,7 @@ struct Ctx {
 };
 
 // misc int slots / red double slots
-enum { M_NSEEK = 0, M_STATUS = 1, M_NS_C = 2, M_NS_K = 3, M_NBAD = 4, M_LSUM = 5, M_WCNT = 8 /* .. +32 */ };
+enum { M_NSEEK = 0, M_STATUS = 1, M_NS_C = 2, M_NS_K = 3, M_NBAD = 4, M_LSUM = 5, M_POOL = 6, M_WCNT = 8 /* .. +32 */ };
 enum { R_SUM = 0, R_MEAN = 32 };
 
 // ---------------------------------------------------------------------------------------------
@@ -237,28 +240,45 @@ __device__ void phase_firm_decisions(Ctx &c)
     }
 }
 
-// a9 firms_fire_workers! (cats.py:379-380): one warp per over-staffed firm; the s employees with
-// the smallest (fire_key, worker index) are dismissed.
-__device__ void phase_fire(Ctx &c, int first, int count)
+// a9 firms_fire_workers! (cats.py:379-380).  A firm with s = Leff - Ld > 0 dismisses the s
+// employees with the smallest (fire_key, worker index).  Step 1 gathers the employees of every
+// over-staffed firm into a pool (one pass over the workers); step 2: one warp per over-staffed
+// firm does s arg-min selections over the pool.  The result does not depend on the pool order.
+__device__ void phase_fire(Ctx &c, int limit)
 {
-    const int W = c.a->L.W;
-    for (int f = first + c.warp; f < first + count; f += c.nwarps) {
+    const Layout &L = c.a->L;
+    const int W = L.W;
+    int *pool_w = reinterpret_cast<int *>(c.sm + L.o_scr);
+    unsigned *pool_k = reinterpret_cast<unsigned *>(c.sm + L.o_scr) + W;
+    if (c.tid == 0) c.misc[M_POOL] = 0;
+    __syncthreads();
+    for (int w = c.tid; w < W; w += c.nt) {
+        int f = c.Oc[w];
+        if (f >= 0 && f < limit && c.vac[f] < 0) {
+            int i = atomicAdd(&c.misc[M_POOL], 1);
+            pool_w[i] = w; pool_k[i] = c.d.fire_key(w);
+        }
+    }
+    __syncthreads();
+    const int n = c.misc[M_POOL];
+    if (n == 0) return;
+    for (int f = c.warp; f < limit; f += c.nwarps) {
         int s = -c.vac[f];
         if (s <= 0) continue;
         for (int r = 0; r < s; ++r) {
             unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
-            for (int w = c.lane; w < W; w += 32) {
+            for (int i = c.lane; i < n; i += 32) {
+                int w = pool_w[i];
                 if (c.Oc[w] == f) {
-                    unsigned key = c.d.fire_key(w);
-                    if (bw == 0x7fffffff || key < bk) { bk = key; bw = w; }  // w increases: ties keep lowest w
+                    unsigned key = pool_k[i];
+                    if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
                 }
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
                 unsigned ok = __shfl_xor_sync(FULL, bk, off);
                 int ow = __shfl_xor_sync(FULL, bw, off);
-                bool take = (ow != 0x7fffffff) && (bw == 0x7fffffff || ok < bk || (ok == bk && ow < bw));
-                if (take) { bk = ok; bw = ow; }
+                if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
             }
             if (bw == 0x7fffffff) break;
             if (c.lane == 0) c.Oc[bw] = -1;
@@ -268,15 +288,19 @@ __device__ void phase_fire(Ctx &c, int first, int count)
     }
 }
 
-// a10 workers_search_job! (cats.py:382)
+// a10 workers_search_job! (cats.py:382).  The unemployed are compacted in visiting order; warp 0
+// then takes 32 of them at a time.  Every lane picks the first of its z_e candidates that still
+// has a vacancy; the longest prefix of lanes whose picks cannot have been pre-empted by a lower
+// lane is committed at once (lane j is safe iff fewer than vac[f] lower lanes chose the same f),
+// the rest retry against the updated vacancies.  Outcome == the sequential visiting-order rule.
+template <int ZM>
 __device__ void phase_job_search(Ctx &c)
 {
     const Layout &L = c.a->L;
-    const int W = L.W, F = L.F, nf = L.F + L.N;
+    const int W = L.W, nf = L.F + L.N;
     const int z = c.d.z_e < nf ? c.d.z_e : nf;
     Order ord; ord.init(c.d, MKT_JOB, W);
-    int *seekers = reinterpret_cast<int *>(c.sm + L.o_seekers);
-    // ordered compaction of the unemployed, in visiting order
+    int *seekers = reinterpret_cast<int *>(c.sm + L.o_scr);
     int total = 0;
     for (int base = 0; base < W; base += c.nt) {
         int pos = base + c.tid, w = -1; bool un = false;
@@ -290,29 +314,37 @@ __device__ void phase_job_search(Ctx &c)
         total += all;
         __syncthreads();
     }
-    // sequential-in-order commit, 32 seekers prepared at a time by warp 0
-    if (c.warp == 0) {
-        for (int base = 0; base < total; base += 32) {
-            int idx = base + c.lane; bool act = idx < total; int w = -1;
-            int cand[MAX_Z];
-            if (act) { w = seekers[idx]; c.d.candidates(PH_JOB, w, nf, z, cand); }
-            unsigned m = __ballot_sync(FULL, act);
-            while (m) {
-                int l = __ffs(m) - 1; m &= m - 1;
-                if (c.lane == l) {
+    if (c.warp != 0) return;
+    const unsigned lt = (1u << c.lane) - 1u;
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + c.lane;
+        int w = -1;
+        int cand[ZM];
+        if (idx < total) { w = seekers[idx]; c.d.candidates<ZM>(PH_JOB, w, nf, z, cand); }
+        unsigned pending = __ballot_sync(FULL, idx < total);
+        while (pending) {
+            const bool mine = (pending >> c.lane) & 1u;
+            int pick = -1;
+            if (mine) {
 #pragma unroll
-                    for (int k = 0; k < MAX_Z; ++k) {
-                        if (k < z && w >= 0) {
-                            int f = cand[k];
-                            if (c.vac[f] > 0) { c.Oc[w] = f; c.Leff[f] += 1; c.vac[f] -= 1; w = -1; }
-                        }
-                    }
-                }
-                __syncwarp();
+                for (int k = 0; k < ZM; ++k)
+                    if (k < z && pick < 0 && c.vac[cand[k]] > 0) pick = cand[k];
             }
+            const bool has = mine && pick >= 0;
+            const unsigned peers = __match_any_sync(FULL, has ? pick : -1 - c.lane);
+            const bool ok = !has || __popc(peers & lt) < c.vac[pick];
+            const unsigned badm = __ballot_sync(FULL, mine && !ok);
+            const unsigned commit = badm ? (pending & ((1u << (__ffs(badm) - 1)) - 1u)) : pending;
+            __syncwarp();
+            if (has && ((commit >> c.lane) & 1u)) {
+                c.Oc[w] = pick;
+                const unsigned grp = peers & commit;
+                if ((grp & lt) == 0) { int n = __popc(grp); c.vac[pick] -= n; c.Leff[pick] += n; }
+            }
+            pending &= ~commit;
+            __syncwarp();
         }
     }
-    (void)F;
 }
 
 // a11 firms_produce! (cats.py:384-385)
@@ -361,6 +393,7 @@ __device__ void phase_produce(Ctx &c)
 }
 
 // a12 capital_goods_market! (cats.py:387)
+template <int ZM>
 __device__ void phase_capital_market(Ctx &c)
 {
     if (c.warp != 0) return;
@@ -373,13 +406,13 @@ __device__ void phase_capital_market(Ctx &c)
     double *inv = c.cf(C_investment), *valinv = c.at(L.o_cvalinv), *wages = c.cf(C_wages);
     for (int base = 0; base < F; base += 32) {
         int pos = base + c.lane, f = -1; bool act = false; double kd = 0.0;
-        int cand[MAX_Z]; double pr[MAX_Z];
+        int cand[ZM]; double pr[ZM];
         if (pos < F) { f = ord.at(pos); kd = Kdem[f]; act = kd > 0.0; }
         if (act) {
-            c.d.candidates(PH_CAP, f, N, z, cand);
+            c.d.candidates<ZM>(PH_CAP, f, N, z, cand);
 #pragma unroll
-            for (int k = 0; k < MAX_Z; ++k) pr[k] = k < z ? Pk[cand[k]] : 0.0;
-            sort_by_price(cand, pr, z);
+            for (int k = 0; k < ZM; ++k) pr[k] = k < z ? Pk[cand[k]] : 0.0;
+            sort_by_price<ZM>(cand, pr, z);
         }
         unsigned m = __ballot_sync(FULL, act);
         while (m) {
@@ -388,7 +421,7 @@ __device__ void phase_capital_market(Ctx &c)
                 double cb = (Ftot[f] + liq[f]) - wages[f];
                 double lq = liq[f], iv = inv[f], vi = valinv[f];
 #pragma unroll
-                for (int k = 0; k < MAX_Z; ++k) {
+                for (int k = 0; k < ZM; ++k) {
                     if (k < z && cb > 0.0 && kd > 0.0) {
                         int best = cand[k];
                         double pk = pr[k];
@@ -423,112 +456,211 @@ __device__ void phase_capital_market(Ctx &c)
     }
 }
 
-// a13 gov_adjusts_subsidy! + a14 workers_get_paid! + a15 households_find_cons_budget!
-// (cats.py:389-393)
-__device__ void phase_income_budget(Ctx &c)
+// a13 gov_adjusts_subsidy! (cats.py:389) and the government side of a14 workers_get_paid!
+// (cats.py:391): subsidy level, wage tax and subsidy totals.  The employed head-count is the sum
+// of Leff (== #{Oc >= 0}: invariant kept by firing, job search and bankruptcy).
+__device__ void phase_gov_income(Ctx &c)
 {
     const Layout &L = c.a->L;
-    const int W = L.W, F = L.F, H = L.H, last = c.last;
-    // phase 17
-    if (c.tid == 0) {
-        double sub = c.par[P_subsidy] * c.scal[S_wb];
-        if (c.par[P_maastricht] > 0.0 && c.scal[S_deficitGDP] > c.par[P_target_deficit]) {
-            double scale = 1.0 - c.par[P_maastricht] * (c.scal[S_deficitGDP] - c.par[P_target_deficit]);
-            if (!(scale > 0.0)) scale = 0.0;
-            sub = sub * scale;
-        }
-        c.scal[S_gov_subsidy_level] = sub;
-    }
-    // employed head-count = sum of Leff (equals #{Oc >= 0}: invariant kept by fire/search/bankrupt)
     if (c.warp == 0) {
         int n = warp_int_sum(L.F + L.N, c.lane, [&](int i) { return c.Leff[i]; });
-        if (c.lane == 0) c.misc[M_LSUM] = n;
-    }
-    __syncthreads();
-    if (last < 18) return;
-    const double wb = c.scal[S_wb], tax = c.par[P_tax_rate], sub = c.scal[S_gov_subsidy_level];
-    const double net = wb * (1.0 - tax);
-    const double xi = c.par[P_xi], chi = c.par[P_chi], price = c.scal[S_price];
-    const double *cdiv = c.cf(C_div_income), *kdiv = c.kf(K_div_income);
-    for (int h = c.tid; h < H; h += c.nt) {
-        double pa = c.PA[h], inc;
-        if (h < W) {
-            inc = c.Oc[h] >= 0 ? net : sub;
-            pa = pa + inc;            // phase 18: workers_get_paid!
-        } else {
-            inc = h < W + F ? cdiv[h - W] : kdiv[h - W - F];
+        if (c.lane == 0) {
+            double sub = c.par[P_subsidy] * c.scal[S_wb];
+            if (c.par[P_maastricht] > 0.0 && c.scal[S_deficitGDP] > c.par[P_target_deficit]) {
+                double scale = 1.0 - c.par[P_maastricht] * (c.scal[S_deficitGDP] - c.par[P_target_deficit]);
+                if (!(scale > 0.0)) scale = 0.0;
+                sub = sub * scale;
+            }
+            c.scal[S_gov_subsidy_level] = sub;
+            if (c.last >= 18) {
+                const double wb = c.scal[S_wb], tax = c.par[P_tax_rate];
+                c.scal[S_gov_TA] = c.scal[S_gov_TA] + (wb * tax) * (double)n;
+                c.scal[S_gov_G] = c.scal[S_gov_G] + sub * (double)(L.W - n);
+            }
         }
-        if (last >= 19) {             // phase 19: households_find_cons_budget!
-            double ir = inc / price;
-            double pm = c.perm[h] * xi + (1.0 - xi) * ir;
-            c.perm[h] = pm;
-            double target = pm + (chi * pa) / price;
-            double b = target * price;
-            if (b > pa) b = pa;
-            if (!(b > 0.0)) b = 0.0;
-            pa = pa - b;
-            c.budget[h] = b;
-        }
-        c.PA[h] = pa;
-    }
-    if (c.tid == 0) {
-        int n_emp = c.misc[M_LSUM];
-        c.scal[S_gov_TA] = c.scal[S_gov_TA] + (wb * tax) * (double)n_emp;
-        c.scal[S_gov_G] = c.scal[S_gov_G] + sub * (double)(W - n_emp);
     }
 }
 
-// a16 consumption_goods_market! (cats.py:394)
+// income and consumption budget of one household (a14 workers_get_paid!, a15
+// households_find_cons_budget!, cats.py:391-393); pa/pm are updated in place, returns the budget
+__device__ __forceinline__ double household_budget(const Ctx &c, int h, double &pa, double &pm, int upto)
+{
+    const Layout &L = c.a->L;
+    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
+    double inc;
+    if (h < L.W) {
+        inc = c.Oc[h] >= 0 ? wb * (1.0 - c.par[P_tax_rate]) : sub;
+        pa = pa + inc;
+    } else {
+        inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
+    }
+    if (upto < 19) return 0.0;
+    const double xi = c.par[P_xi], chi = c.par[P_chi];
+    double ir = inc / price;
+    pm = pm * xi + (1.0 - xi) * ir;
+    double target = pm + (chi * pa) / price;
+    double b = target * price;
+    if (b > pa) b = pa;
+    if (!(b > 0.0)) b = 0.0;
+    pa = pa - b;
+    return b;
+}
+
+// debug path only (stop_phase 18 / 19): the household rules without the market
+__device__ void phase_households_only(Ctx &c)
+{
+    for (int h = c.tid; h < c.a->L.H; h += c.nt) {
+        double pa = c.PA[h], pm = c.perm[h];
+        household_budget(c, h, pa, pm, c.last);
+        c.PA[h] = pa; c.perm[h] = pm;
+    }
+}
+
+// One consumption-goods seller as the market sees it.  The SoA rows (P, Yd, Q, stock) are packed
+// into this 32-byte record when the market opens and unpacked when it closes, so that a visit is
+// one shared-memory round trip instead of three dependent ones.
+struct __align__(16) MktRec { double ys, yd, q, p; };
+
+// a14 + a15 + a16 consumption_goods_market! (cats.py:391-394), fused and warp-specialised.
+//
+// Households are visited in the market's random order, 32 ("a chunk") at a time.
+//   producers (warps 1..): for one chunk each, every lane pulls its household's wealth and
+//       permanent income from global memory, computes income and budget (a14, a15), draws the z_c
+//       candidate firms (Philox), sorts them by price and pre-divides the demand b/P it would
+//       express at each -- then publishes the chunk in a shared-memory slot (mbarrier "full").
+//   consumer (warp 0): takes the chunks in order and lets the lanes commit one after the other in
+//       visiting order against the sellers' records -- the sequential-market rule of the reference.
+//       All candidate records of a buyer are pulled up front, so a turn is one smem round trip.
+// The serial chain is what bounds an economy-period; the producers keep everything that does not
+// depend on market state off it.
+struct GoodsSlot {            // one chunk of 32 prepared buyers, SoA over lanes
+    double b[32];             // budget
+    double pa[32];            // wealth after the budget was set aside
+    double dk[MAX_Z][32];     // demand b / P at the k-th cheapest candidate
+    unsigned long long cl[2][32];  // candidate firm ids, 16 bit each: k = 0..3 in cl[0], 4..7 in cl[1]
+    int h[32];                // household id (-1: no household in this lane)
+};
+
+static_assert(sizeof(GoodsSlot) == 32 * (8 + 8 + 8 * MAX_Z + 16 + 4), "GoodsSlot must match cats_layout.h o_ring sizing");
+
+template <int ZM>
 __device__ void phase_goods_market(Ctx &c)
 {
-    if (c.warp != 0) return;
     const Layout &L = c.a->L;
     const int F = L.F, H = L.H;
     const int z = c.d.z_c < F ? c.d.z_c : F;
-    Order ord; ord.init(c.d, MKT_GOODS, H);
-    double *P = c.cf(C_P), *Yd = c.cf(C_Yd), *Q = c.cf(C_Q), *Ys = c.at(L.o_cYstock);
-    for (int base = 0; base < H; base += 32) {
-        int pos = base + c.lane, h = -1; bool act = false; double b = 0.0;
-        int cand[MAX_Z]; double pr[MAX_Z];
-        if (pos < H) { h = ord.at(pos); b = c.budget[h]; act = b > 0.0; }
-        double d0 = 0.0;
-        if (act) {
-            c.d.candidates(PH_GOODS, h, F, z, cand);
+    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.o_scr);
+    {
+        const double *P = c.cf(C_P), *Ys = c.at(L.o_cYstock);
+        for (int f = c.tid; f < F; f += c.nt) { MktRec r; r.ys = Ys[f]; r.yd = 0.0; r.q = 0.0; r.p = P[f]; mkt[f] = r; }
+    }
+    __syncthreads();
+    const int nchunks = (H + 31) / 32;
+    const int nprod = c.nwarps - 1;
+    unsigned char *slots = c.sm + L.o_ring;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(c.sm + L.o_misc + 128);  // full[s] = bars[2s], empty[s] = bars[2s+1]
+    if (c.warp > 0) {
+        // ---------------- producer ----------------
+        const int s = c.warp - 1;
+        GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
+        Order ord; ord.init(c.d, MKT_GOODS, H);
+        for (int ch = s; ch < nchunks; ch += nprod) {
+            const int pos = ch * 32 + c.lane;
+            int h = -1; double pa = 0.0, pm = 0.0, b = 0.0;
+            int cand[ZM]; double pr[ZM], dk[ZM];
+            unsigned long long cl0 = 0ull, cl1 = 0ull;
 #pragma unroll
-            for (int k = 0; k < MAX_Z; ++k) pr[k] = k < z ? P[cand[k]] : 0.0;
-            sort_by_price(cand, pr, z);
-            d0 = b / pr[0];
+            for (int k = 0; k < ZM; ++k) dk[k] = 0.0;
+            if (pos < H) {
+                h = ord.at(pos);
+                pa = c.PA[h]; pm = c.perm[h];
+                b = household_budget(c, h, pa, pm, 99);
+                c.perm[h] = pm;
+            }
+            if (b > 0.0) {
+                c.d.candidates<ZM>(PH_GOODS, h, F, z, cand);
+#pragma unroll
+                for (int k = 0; k < ZM; ++k) pr[k] = k < z ? mkt[cand[k]].p : 1.0;
+                sort_by_price<ZM>(cand, pr, z);
+#pragma unroll
+                for (int k = 0; k < ZM; ++k) {
+                    dk[k] = b / pr[k];
+                    if (k < z) { if (k < 4) cl0 |= (unsigned long long)(unsigned)cand[k] << (16 * k); else cl1 |= (unsigned long long)(unsigned)cand[k] << (16 * (k - 4)); }
+                }
+            }
+            mbar_wait(&bars[2 * s + 1], ((c.par_empty >> s) & 1u) ^ 1u);   // slot free?
+            c.par_empty ^= 1u << s;
+            slot->b[c.lane] = b; slot->pa[c.lane] = pa; slot->cl[0][c.lane] = cl0; slot->cl[1][c.lane] = cl1; slot->h[c.lane] = h;
+#pragma unroll
+            for (int k = 0; k < ZM; ++k) slot->dk[k][c.lane] = dk[k];
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&bars[2 * s]);                       // publish
         }
-        unsigned m = __ballot_sync(FULL, act);
-        while (m) {
-            int l = __ffs(m) - 1; m &= m - 1;
-            if (c.lane == l) {
+    } else {
+        // ---------------- consumer ----------------
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % nprod;
+            GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
+            mbar_wait(&bars[2 * s], (c.par_full >> s) & 1u);
+            c.par_full ^= 1u << s;
+            double b = slot->b[c.lane];
+            const double pa = slot->pa[c.lane];
+            const unsigned long long cl0 = slot->cl[0][c.lane], cl1 = ZM > 4 ? slot->cl[1][c.lane] : 0ull;
+            auto firm_of = [&](int k) -> unsigned { return k < 4 ? (unsigned)(cl0 >> (16 * k)) & 0xffffu : (unsigned)(cl1 >> (16 * (k - 4))) & 0xffffu; };
+            const int h = slot->h[c.lane];
+            double dk[ZM];
 #pragma unroll
-                for (int k = 0; k < MAX_Z; ++k) {
-                    if (k < z && b > 0.0) {
-                        int best = cand[k];
-                        double p = pr[k];
-                        double d = k == 0 ? d0 : b / p;
-                        Yd[best] = Yd[best] + d;
-                        double ys = Ys[best];
-                        if (ys > 0.0) {
-                            if (ys > d) {
-                                Ys[best] = ys - d;
-                                Q[best] = Q[best] + d;
-                                b = 0.0;
-                            } else {
-                                b = b - ys * p;
-                                Q[best] = Q[best] + ys;
-                                Ys[best] = 0.0;
+            for (int k = 0; k < ZM; ++k) dk[k] = slot->dk[k][c.lane];
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&bars[2 * s + 1]);                   // slot may be refilled
+            unsigned m = __ballot_sync(FULL, b > 0.0);
+            while (m) {
+                const int l = __ffs(m) - 1; m &= m - 1;
+                if (c.lane == l) {
+                    double ys[ZM], yd[ZM], q[ZM];
+#pragma unroll
+                    for (int k = 0; k < ZM; ++k) {
+                        if (k < z) {
+                            const MktRec *r = &mkt[firm_of(k)];
+                            double2 a0 = *reinterpret_cast<const double2 *>(r);
+                            ys[k] = a0.x; yd[k] = a0.y; q[k] = r->q;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < ZM; ++k) {
+                        if (k < z && b > 0.0) {
+                            MktRec *r = &mkt[firm_of(k)];
+                            const double d = dk[k];
+                            yd[k] = yd[k] + d;
+                            if (ys[k] > 0.0) {
+                                if (ys[k] > d) {
+                                    ys[k] = ys[k] - d;
+                                    q[k] = q[k] + d;
+                                    b = 0.0;
+                                } else {
+                                    const double p = r->p;
+                                    b = b - ys[k] * p;
+                                    q[k] = q[k] + ys[k];
+                                    ys[k] = 0.0;
+#pragma unroll
+                                    for (int kk = k + 1; kk < ZM; ++kk)       // rare: partial fill
+                                        if (kk < z) dk[kk] = b / mkt[firm_of(kk)].p;
+                                }
                             }
+                            *reinterpret_cast<double2 *>(r) = make_double2(ys[k], yd[k]);
+                            r->q = q[k];
                         }
                     }
                 }
-                c.PA[h] = c.PA[h] + b;
-                c.budget[h] = b;
+                __syncwarp();
             }
-            __syncwarp();
+            if (h >= 0) c.PA[h] = pa + b;
         }
+    }
+    __syncthreads();
+    {
+        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q), *Ys = c.at(L.o_cYstock);
+        for (int f = c.tid; f < F; f += c.nt) { MktRec r = mkt[f]; Ys[f] = r.ys; Yd[f] = r.yd; Q[f] = r.q; }
     }
 }
 
@@ -851,10 +983,14 @@ __device__ void phase_closing(Ctx &c)
 
 // ---------------------------------------------------------------------------------------------
 // one period; phase ids as docs/MODEL.md section 6 (stop_phase halts after the given id)
+template <int ZM>
 __device__ void run_period(Ctx &c)
 {
     const KArgs &a = *c.a;
     const int F = a.L.F, N = a.L.N, last = c.last;
+    long long t0 = 0;
+    if (a.cycles && c.tid == 0 && blockIdx.x == 0) t0 = clock64();
+#define TICK(slot) do { if (a.cycles && c.tid == 0 && blockIdx.x == 0) { long long t1 = clock64(); a.cycles[slot] += t1 - t0; t0 = t1; } } while (0)
     // phases 1-2: reset_gov_and_banking_variables!, set_bond_interest_rate! (cats.py:355-356)
     if (c.tid == 0) {
         c.scal[S_gov_TA] = 0.0; c.scal[S_gov_G] = 0.0;
@@ -866,44 +1002,57 @@ __device__ void run_period(Ctx &c)
     if (last < 3) return;
     phase_firm_decisions(c);  // 3..10
     __syncthreads();
+    TICK(0);
     if (last < 11) return;
-    phase_fire(c, 0, F);      // 11
-    if (last >= 12) phase_fire(c, F, N);  // 12 (disjoint firms and workers: no barrier needed between)
+    phase_fire(c, last >= 12 ? F + N : F);  // 11, 12
     __syncthreads();
+    TICK(1);
     if (last < 13) return;
-    phase_job_search(c);      // 13
+    phase_job_search<ZM>(c);  // 13
     __syncthreads();
+    TICK(2);
     if (last < 14) return;
     phase_produce(c);         // 14, 15
     __syncthreads();
+    TICK(3);
     if (last < 16) return;
-    phase_capital_market(c);  // 16
+    phase_capital_market<ZM>(c);  // 16
     __syncthreads();
+    TICK(4);
     if (last < 17) return;
-    phase_income_budget(c);   // 17, 18, 19
+    phase_gov_income(c);      // 17 (+ government side of 18)
     __syncthreads();
-    if (last < 20) return;
-    phase_goods_market(c);    // 20
+    TICK(5);
+    if (last < 18) return;
+    if (last < 20) { phase_households_only(c); __syncthreads(); return; }
+    phase_goods_market<ZM>(c);  // 18, 19, 20
     __syncthreads();
+    TICK(6);
     if (last < 21) return;
     phase_accounting(c);      // 21, 22
     __syncthreads();
+    TICK(7);
     if (last < 23) return;
     phase_reward(c);          // 23
     __syncthreads();
+    TICK(8);
     if (last < 24) return;
     phase_tracking(c);        // 24
     __syncthreads();
+    TICK(9);
     if (last < 25) return;
     phase_bankrupt(c);        // 25
     __syncthreads();
+    TICK(10);
     if (last < 26) return;
     phase_closing(c);         // 26..29
     __syncthreads();
+    TICK(11);
+#undef TICK
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) cats_period_kernel(const __grid_constant__ KArgs a)
+template <int NT, int ZM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout &L = a.L;
@@ -915,9 +1064,6 @@ __global__ void __launch_bounds__(NT) cats_period_kernel(const __grid_constant__
     c.Ld = reinterpret_cast<int *>(smem + L.o_Ld);
     c.vac = reinterpret_cast<int *>(smem + L.o_vac);
     c.Oc = reinterpret_cast<int *>(smem + L.o_Oc);
-    c.PA = reinterpret_cast<double *>(smem + L.o_PA);
-    c.perm = reinterpret_cast<double *>(smem + L.o_perm);
-    c.budget = reinterpret_cast<double *>(smem + L.o_budget);
     c.red = reinterpret_cast<double *>(smem + L.o_red);
     c.misc = reinterpret_cast<int *>(smem + L.o_misc);
     c.bad = smem + L.o_bad;
@@ -926,25 +1072,33 @@ __global__ void __launch_bounds__(NT) cats_period_kernel(const __grid_constant__
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.o_misc + 192);
 
-    if (c.tid == 0) mbar_init(bar, 1);
+    c.par_full = 0u; c.par_empty = 0u;
+    if (c.tid == 0) {
+        mbar_init(bar, 1);
+        uint64_t *ring = reinterpret_cast<uint64_t *>(smem + L.o_misc + 128);
+        for (int i = 0; i < 2 * (NT / 32 - 1); ++i) mbar_init(&ring[i], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
     uint32_t parity = 0;
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         c.b = b;
         unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
-        // HBM -> smem: one TMA bulk copy of the whole economy
+        c.PA = reinterpret_cast<double *>(blob + L.o_PA);
+        c.perm = reinterpret_cast<double *>(blob + L.o_perm);
+        // HBM -> smem: one TMA bulk copy of the resident prefix (firm tables, employment links)
         if (c.tid == 0) {
             fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)L.blob);
-            bulk_g2s(smem, blob, (uint32_t)L.blob, bar);
+            mbar_expect_tx(bar, (uint32_t)L.resident);
+            bulk_g2s(smem, blob, (uint32_t)L.resident, bar);
         }
         // parameters (shared row or per-economy row) while the copy is in flight
         const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
         for (int i = c.tid; i < N_PARAMS; i += NT) c.par[i] = pr[i];
         if (c.tid == 0) c.par[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
         // zero the transients so that debug images are deterministic
-        for (int i = L.blob / 4 + c.tid; i < L.workset / 4; i += NT) reinterpret_cast<int *>(smem)[i] = 0;
+        for (int i = L.resident / 4 + c.tid; i < L.workset / 4; i += NT) reinterpret_cast<int *>(smem)[i] = 0;
         mbar_wait(bar, parity);
         parity ^= 1u;
         __syncthreads();
@@ -957,7 +1111,7 @@ __global__ void __launch_bounds__(NT) cats_period_kernel(const __grid_constant__
         for (int t = 0; t < a.n_periods; ++t) {
             c.d.period = (uint32_t)c.scal[S_timestep];
             c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
-            run_period(c);
+            run_period<ZM>(c);
             __syncthreads();
             if (a.stats && c.tid < N_STATS) {
                 const double *s = c.scal;
@@ -1000,11 +1154,11 @@ __global__ void __launch_bounds__(NT) cats_period_kernel(const __grid_constant__
             int4 *dst = reinterpret_cast<int4 *>(a.debug + (size_t)b * (size_t)L.workset);
             for (int i = c.tid; i < L.workset / 16; i += NT) dst[i] = src[i];
         }
-        // smem -> HBM: bulk store of the blob image
+        // smem -> HBM: bulk store of the resident prefix
         fence_proxy_async();
         __syncthreads();
         if (c.tid == 0) {
-            bulk_s2g(blob, smem, (uint32_t)L.blob);
+            bulk_s2g(blob, smem, (uint32_t)L.resident);
             bulk_commit();
             bulk_wait_all();
         }
@@ -1056,7 +1210,15 @@ using namespace cats;
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
-constexpr int kThreads = 256;
+static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
+constexpr int kThreads = 128;   // threads per economy block
+constexpr int kMinBlocks = 4;   // __launch_bounds__ hint: register budget for >= 4 resident economies / SM
+typedef void (*KernelFn)(const KArgs);
+static KernelFn select_kernel(int max_z)
+{
+    if (max_z > 0 && max_z <= 5) return cats_period_kernel<kThreads, 5, kMinBlocks>;
+    return cats_period_kernel<kThreads, MAX_Z, kMinBlocks>;
+}
 
 static int fail(int code, const char *fmt, const char *detail)
 {
@@ -1067,7 +1229,7 @@ static int fail(int code, const char *fmt, const char *detail)
 static int check_sizes(int W, int F, int N)
 {
     if (W < 1 || F < 1 || N < 1) return fail(CATS_EINVAL, "W, F, N must be >= 1%s", "");
-    if ((long long)W + F + N > (1 << 24)) return fail(CATS_EINVAL, "economy too large%s", "");
+    if ((long long)W + F + N > (1 << 24) || F + N > 65535) return fail(CATS_EINVAL, "economy too large%s", "");
     return CATS_OK;
 }
 
@@ -1091,6 +1253,7 @@ extern "C" {
 int cats_abi_version(void) { return CATS_ABI_VERSION; }
 const char *cats_last_error(void) { return g_err; }
 uint64_t cats_launch_count(void) { return g_launches.load(); }
+void cats_debug_phase_cycles(void *d_cycles16) { g_cycles = (long long *)d_cycles16; }
 
 size_t cats_blob_bytes(int W, int F, int N)
 {
@@ -1141,7 +1304,6 @@ int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byt
         {"c_Ftot", (uint64_t)L.o_cFtot, F, 0}, {"c_Kdem", (uint64_t)L.o_cKdem, F, 0},
         {"c_Ystock", (uint64_t)L.o_cYstock, F, 0}, {"c_valinv", (uint64_t)L.o_cvalinv, F, 0},
         {"k_Ftot", (uint64_t)L.o_kFtot, N, 0}, {"k_Ystock", (uint64_t)L.o_kYstock, N, 0},
-        {"budget", (uint64_t)L.o_budget, L.H, 0},
     };
     for (auto &e : t)
         if (!strcmp(name, e.n)) { *byte_offset = e.off; *count = e.cnt; *dtype = e.dt; return CATS_OK; }
@@ -1163,7 +1325,7 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
     return CATS_OK;
 }
 
-static int configure_kernel(const Layout &L, int *blocks_per_sm, int *num_sms)
+static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, int *num_sms)
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -1171,10 +1333,10 @@ static int configure_kernel(const Layout &L, int *blocks_per_sm, int *num_sms)
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (L.smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
-    e = cudaFuncSetAttribute(cats_period_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cats_period_kernel<kThreads>, kThreads, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, L.smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1189,7 +1351,7 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
     if (int rc = check_sizes(W, F, N)) return rc;
     Layout L = make_layout(W, F, N);
     int occ = 0, sms = 0;
-    if (int rc = configure_kernel(L, &occ, &sms)) return rc;
+    if (int rc = configure_kernel(L, select_kernel(5), &occ, &sms)) return rc;
     if (threads) *threads = kThreads;
     if (smem_bytes) *smem_bytes = L.smem;
     if (blocks_per_sm) *blocks_per_sm = occ;
@@ -1220,6 +1382,7 @@ int cats_step(const cats_step_args *s)
     if (!s->d_blobs || !s->d_params || s->B < 0) return fail(CATS_EINVAL, "cats_step: null pointer or negative B%s", "");
     if (s->params_stride != 0 && s->params_stride < CATS_N_PARAMS) return fail(CATS_EINVAL, "params_stride must be 0 or >= 34%s", "");
     if (s->n_periods < 1) return fail(CATS_EINVAL, "n_periods must be >= 1%s", "");
+    if (s->max_z < 0 || s->max_z > CATS_MAX_Z) return fail(CATS_EINVAL, "max_z must be in [0, 8]%s", "");
     if (s->n_agents < 0 || s->n_agents > s->F) return fail(CATS_EINVAL, "n_agents must be in [0, F]%s", "");
     if (s->n_periods > 1 && s->n_agents > 0 && !(s->flags & CATS_FLAG_BURNIN) && s->d_actions)
         return fail(CATS_EINVAL, "multi-period launches take no actions (use the BURNIN flag)%s", "");
@@ -1240,14 +1403,16 @@ int cats_step(const cats_step_args *s)
     a.obs = s->d_obs; a.reward = s->d_reward; a.terminated = s->d_terminated; a.status = s->d_status;
     a.stats = s->d_stats; a.tape = s->d_tape; a.stop_phase = s->stop_phase;
     a.debug = (unsigned char *)s->d_debug;
+    a.cycles = g_cycles;
     if (s->d_tape) {
         a.T = make_tape(s->W, s->F, s->N, s->tape_z[0], s->tape_z[1], s->tape_z[2]);
     }
     int occ = 0, sms = 0;
-    if (int rc = configure_kernel(a.L, &occ, &sms)) return rc;
+    KernelFn fn = select_kernel(s->max_z);
+    if (int rc = configure_kernel(a.L, fn, &occ, &sms)) return rc;
     long long grid = (long long)occ * sms;
     if (grid > s->B) grid = s->B;
-    cats_period_kernel<kThreads><<<(unsigned)grid, kThreads, a.L.smem, (cudaStream_t)s->stream>>>(a);
+    fn<<<(unsigned)grid, kThreads, a.L.smem, (cudaStream_t)s->stream>>>(a);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));

@@ -1,9 +1,16 @@
 // cats_layout.h -- economy blob / on-chip working-set layout shared by host and device code.
 //
-// One economy = one contiguous blob in HBM (docs/MODEL.md section 2, docs/DESIGN.md "data layout").
-// The shared-memory working set of the period kernel starts with a byte-identical image of the
-// blob (so the HBM<->smem transfer is a single bulk copy) followed by the transients that live
-// inside one period only.  All section offsets are multiples of 16 bytes (bulk-copy granularity).
+// One economy = one contiguous blob in HBM (docs/MODEL.md section 2, docs/DESIGN.md "data layout"):
+//
+//   [ scal | C-firm rows | K-firm rows | Leff | Oc |  PA | perm ]
+//     `------------- resident prefix -------------'  `- household tail -'
+//
+// The resident prefix (firm tables, employment links: everything the matching markets touch at
+// random) is pulled into shared memory with one TMA bulk copy and pushed back with one bulk store.
+// The household tail (wealth, permanent income) is streamed from global memory / L2 once per
+// period inside the consumption-goods loop.  Keeping it out of shared memory is what lets ~6
+// economies be resident per SM instead of 3, and the step is latency-bound, so that is throughput.
+// All section offsets are multiples of 16 bytes (bulk-copy granularity).
 #pragma once
 #include <stdint.h>
 
@@ -45,12 +52,11 @@ struct Layout {
     int32_t W, F, N, H;
     int32_t rowF, rowN;  // bytes of one firm f64 row
     // persisted sections (byte offsets inside the blob)
-    int32_t o_scal, o_c, o_k, o_Leff, o_PA, o_perm, o_Oc, blob;
-    // transients (byte offsets inside the working set; all >= blob)
-    int32_t o_Ld, o_vac, o_cFtot, o_cKdem, o_cYstock, o_cvalinv, o_kFtot, o_kYstock, o_budget,
-        workset;
+    int32_t o_scal, o_c, o_k, o_Leff, o_Oc, resident, o_PA, o_perm, blob;
+    // transients (byte offsets inside the shared-memory working set; all >= resident)
+    int32_t o_Ld, o_vac, o_cFtot, o_cKdem, o_cYstock, o_cvalinv, o_kFtot, o_kYstock, workset;
     // scratch that is never dumped
-    int32_t o_seekers, o_bad, o_red, o_par, o_misc, smem;
+    int32_t o_scr, scr_bytes, o_ring, o_bad, o_red, o_par, o_misc, smem;
 };
 
 __host__ __device__ inline int32_t up16(int64_t x) { return (int32_t)((x + 15) & ~(int64_t)15); }
@@ -65,11 +71,15 @@ inline Layout make_layout(int W, int F, int N)
     L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
     L.o_k = (int32_t)o; o += (int64_t)NK_FIELDS * L.rowN;
     L.o_Leff = (int32_t)o; o += up16(4ll * (F + N));
-    L.o_PA = (int32_t)o; o += up16(8ll * L.H);
-    L.o_perm = (int32_t)o; o += up16(8ll * L.H);
     L.o_Oc = (int32_t)o; o += up16(4ll * W);
     o = (o + 127) & ~(int64_t)127;
+    L.resident = (int32_t)o;
+    L.o_PA = (int32_t)o; o += up16(8ll * L.H);
+    L.o_perm = (int32_t)o; o += up16(8ll * L.H);
+    o = (o + 127) & ~(int64_t)127;
     L.blob = (int32_t)o;
+    // shared-memory image: [0, resident) mirrors the blob prefix, transients follow
+    o = L.resident;
     L.o_Ld = (int32_t)o; o += up16(4ll * (F + N));
     L.o_vac = (int32_t)o; o += up16(4ll * (F + N));
     L.o_cFtot = (int32_t)o; o += L.rowF;
@@ -78,9 +88,12 @@ inline Layout make_layout(int W, int F, int N)
     L.o_cvalinv = (int32_t)o; o += L.rowF;
     L.o_kFtot = (int32_t)o; o += L.rowN;
     L.o_kYstock = (int32_t)o; o += L.rowN;
-    L.o_budget = (int32_t)o; o += up16(8ll * L.H);
     L.workset = (int32_t)o;
-    L.o_seekers = (int32_t)o; o += up16(4ll * W);
+    // scratch: fire pool (W x {worker, key}) / job seekers (W ints) / goods-market records (F x 32 B)
+    // -- used at different times
+    L.o_scr = (int32_t)o; L.scr_bytes = up16(8ll * W > 32ll * F ? 8ll * W : 32ll * F); o += L.scr_bytes;
+    // goods-market producer/consumer ring: 3 slots of 32 prepared buyers (see GoodsSlot)
+    L.o_ring = (int32_t)o; o += 3 * (32 * (8 + 8 + 8 * MAX_Z + 16 + 4));
     L.o_bad = (int32_t)o; o += up16(F + N);
     L.o_red = (int32_t)o; o += 8 * 64;
     L.o_par = (int32_t)o; o += 8 * P_SLOTS;

@@ -63,6 +63,7 @@ class BatchedCats:
             self._params_t = torch.tensor([params_vector(d) for d in dicts], dtype=torch.float64,
                                           device=self.device)
             self._params_stride = nat.N_PARAMS
+            self._max_z = max(max(int(d[k]) for k in ("z_c", "z_k", "z_e")) for d in dicts)
         else:
             self.params = load_parameters(params)
             validate(self.params, F, N)
@@ -70,6 +71,7 @@ class BatchedCats:
             self._params_t = torch.tensor(params_vector(self.params), dtype=torch.float64,
                                           device=self.device)
             self._params_stride = 0
+            self._max_z = max(self._z)
 
         self.blob_bytes = int(self._lib.cats_blob_bytes(W, F, N))
         if self.blob_bytes == 0:
@@ -153,6 +155,7 @@ class BatchedCats:
                 raise ValueError("tape replay needs the same z_c, z_k, z_e in every economy")
             a.d_tape = tape.data_ptr()
             a.tape_z[0], a.tape_z[1], a.tape_z[2] = self._z
+        a.max_z = self._max_z
         a.stop_phase = stop_phase
         a.d_debug = debug.data_ptr() if debug is not None else None
         a.stream = self._stream()

@@ -7,7 +7,7 @@ from oracle import oracle as orc
 
 PERSISTED = (["scal", "PA", "perm"] + ["c_" + f for f in orc.C_FIELDS] + ["k_" + f for f in orc.K_FIELDS])
 PERSISTED_I32 = ["c_Leff", "k_Leff", "Oc"]
-TRANSIENT_F64 = ["c_Ftot", "c_Kdem", "c_Ystock", "c_valinv", "k_Ftot", "k_Ystock", "budget"]
+TRANSIENT_F64 = ["c_Ftot", "c_Kdem", "c_Ystock", "c_valinv", "k_Ftot", "k_Ystock"]
 TRANSIENT_I32 = ["c_Ld", "c_vac", "k_Ld", "k_vac"]
 
 

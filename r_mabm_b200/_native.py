@@ -6,10 +6,13 @@ command, and every compute entry point needs a CUDA device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libcats_b200.so"
+if os.environ.get("CATS_B200_LIB"):  # development aid: load an experimental build of the same ABI
+    LIB_PATH = Path(os.environ["CATS_B200_LIB"]).resolve()
 
 N_PARAMS = 34
 N_SCAL = 32

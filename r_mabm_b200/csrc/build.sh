@@ -4,7 +4,7 @@
 # what makes the kernels bit-exact against the CPU oracle.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-out="${here}/../libcats_b200.so"
+out="${CATS_OUT:-${here}/../libcats_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
     -Xcompiler -fPIC -shared ${CATS_NVCC_EXTRA:-} \

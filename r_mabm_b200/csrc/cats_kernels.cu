@@ -22,6 +22,13 @@
 #include "cats_device.cuh"
 #include "cats_layout.h"
 
+#ifndef CATS_GOODS_BACKOFF
+#define CATS_GOODS_BACKOFF 1
+#endif
+#ifndef CATS_GOODS_FASTPATH
+#define CATS_GOODS_FASTPATH 1
+#endif
+
 namespace cats {
 
 struct KArgs {
@@ -53,6 +60,7 @@ struct KArgs {
 // per-block view of the shared-memory working set
 struct Ctx {
     unsigned char *sm;
+    unsigned char *blob;  // this economy's blob in global memory (C-firm rows, PA, perm live there)
     const KArgs *a;
     double *scal, *par;
     int *Leff, *Ld, *vac, *Oc;
@@ -63,9 +71,9 @@ struct Ctx {
     int tid, lane, warp, nwarps, nt;
     long long b;  // economy index inside this launch
     int last;     // last phase id to execute (stop_phase or 99)
-    unsigned par_full, par_empty;  // mbarrier phase parities of the goods-market ring (bit s = slot s)
+    unsigned goods_epoch;  // goods markets run so far by this block (mbarrier phase bookkeeping)
     Draws d;
-    __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_c + field * a->L.rowF); }
+    __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + a->L.o_c + field * a->L.rowF); }  // GLOBAL
     __device__ __forceinline__ double *kf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_k + field * a->L.rowN); }
     __device__ __forceinline__ double *at(int off) const { return reinterpret_cast<double *>(sm + off); }
 };
@@ -537,11 +545,11 @@ struct GoodsSlot {            // one chunk of 32 prepared buyers, SoA over lanes
     double b[32];             // budget
     double pa[32];            // wealth after the budget was set aside
     double dk[MAX_Z][32];     // demand b / P at the k-th cheapest candidate
-    unsigned long long cl[2][32];  // candidate firm ids, 16 bit each: k = 0..3 in cl[0], 4..7 in cl[1]
+    int off[MAX_Z][32];       // shared-memory byte offset of the k-th candidate's MktRec (dummy record if k >= z)
     int h[32];                // household id (-1: no household in this lane)
 };
-
-static_assert(sizeof(GoodsSlot) == 32 * (8 + 8 + 8 * MAX_Z + 16 + 4), "GoodsSlot must match cats_layout.h o_ring sizing");
+static_assert(sizeof(GoodsSlot) == 32 * (8 + 8 + 8 * MAX_Z + 4 * MAX_Z + 4), "GoodsSlot must match cats_layout.h o_ring sizing");
+constexpr int GOODS_SLOTS = 2;
 
 template <int ZM>
 __device__ void phase_goods_market(Ctx &c)
@@ -549,10 +557,12 @@ __device__ void phase_goods_market(Ctx &c)
     const Layout &L = c.a->L;
     const int F = L.F, H = L.H;
     const int z = c.d.z_c < F ? c.d.z_c : F;
-    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.o_scr);
+    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.o_scr);   // F records + 1 dummy
     {
         const double *P = c.cf(C_P), *Ys = c.at(L.o_cYstock);
-        for (int f = c.tid; f < F; f += c.nt) { MktRec r; r.ys = Ys[f]; r.yd = 0.0; r.q = 0.0; r.p = P[f]; mkt[f] = r; }
+        for (int f = c.tid; f <= F; f += c.nt) {
+            MktRec r; r.ys = f < F ? Ys[f] : 0.0; r.yd = 0.0; r.q = 0.0; r.p = f < F ? P[f] : 1.0; mkt[f] = r;
+        }
     }
     __syncthreads();
     const int nchunks = (H + 31) / 32;
@@ -560,17 +570,16 @@ __device__ void phase_goods_market(Ctx &c)
     unsigned char *slots = c.sm + L.o_ring;
     uint64_t *bars = reinterpret_cast<uint64_t *>(c.sm + L.o_misc + 128);  // full[s] = bars[2s], empty[s] = bars[2s+1]
     if (c.warp > 0) {
-        // ---------------- producer ----------------
-        const int s = c.warp - 1;
-        GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
+        // ---------------- producers: chunk ch goes to slot ch % GOODS_SLOTS, made by warp 1 + ch % nprod
         Order ord; ord.init(c.d, MKT_GOODS, H);
-        for (int ch = s; ch < nchunks; ch += nprod) {
+        for (int ch = c.warp - 1; ch < nchunks; ch += nprod) {
+            const int s = ch % GOODS_SLOTS;
+            GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
             const int pos = ch * 32 + c.lane;
             int h = -1; double pa = 0.0, pm = 0.0, b = 0.0;
             int cand[ZM]; double pr[ZM], dk[ZM];
-            unsigned long long cl0 = 0ull, cl1 = 0ull;
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) dk[k] = 0.0;
+            for (int k = 0; k < ZM; ++k) { dk[k] = 0.0; cand[k] = F; }
             if (pos < H) {
                 h = ord.at(pos);
                 pa = c.PA[h]; pm = c.perm[h];
@@ -583,72 +592,62 @@ __device__ void phase_goods_market(Ctx &c)
                 for (int k = 0; k < ZM; ++k) pr[k] = k < z ? mkt[cand[k]].p : 1.0;
                 sort_by_price<ZM>(cand, pr, z);
 #pragma unroll
-                for (int k = 0; k < ZM; ++k) {
-                    dk[k] = b / pr[k];
-                    if (k < z) { if (k < 4) cl0 |= (unsigned long long)(unsigned)cand[k] << (16 * k); else cl1 |= (unsigned long long)(unsigned)cand[k] << (16 * (k - 4)); }
-                }
+                for (int k = 0; k < ZM; ++k) { dk[k] = k < z ? b / pr[k] : 0.0; if (k >= z) cand[k] = F; }
             }
-            mbar_wait(&bars[2 * s + 1], ((c.par_empty >> s) & 1u) ^ 1u);   // slot free?
-            c.par_empty ^= 1u << s;
-            slot->b[c.lane] = b; slot->pa[c.lane] = pa; slot->cl[0][c.lane] = cl0; slot->cl[1][c.lane] = cl1; slot->h[c.lane] = h;
+            // wait until the consumer has drained the previous occupant of this slot
+            const unsigned use = c.goods_epoch * (unsigned)((nchunks + GOODS_SLOTS - 1 - s) / GOODS_SLOTS) + (unsigned)(ch / GOODS_SLOTS);  // n-th use of the slot since kernel start
+            mbar_wait_backoff(&bars[2 * s + 1], (use & 1u) ^ 1u);
+            slot->b[c.lane] = b; slot->pa[c.lane] = pa; slot->h[c.lane] = h;
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) slot->dk[k][c.lane] = dk[k];
+            for (int k = 0; k < ZM; ++k) { slot->dk[k][c.lane] = dk[k]; slot->off[k][c.lane] = cand[k] * (int)sizeof(MktRec); }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(&bars[2 * s]);                       // publish
+            if (c.lane == 0) mbar_arrive(&bars[2 * s]);                  // publish
         }
     } else {
         // ---------------- consumer ----------------
+        unsigned char *mbase = reinterpret_cast<unsigned char *>(mkt);
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % nprod;
+            const int s = ch % GOODS_SLOTS;
             GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
-            mbar_wait(&bars[2 * s], (c.par_full >> s) & 1u);
-            c.par_full ^= 1u << s;
+            mbar_wait(&bars[2 * s], (c.goods_epoch * (unsigned)((nchunks + GOODS_SLOTS - 1 - s) / GOODS_SLOTS) + (unsigned)(ch / GOODS_SLOTS)) & 1u);
             double b = slot->b[c.lane];
             const double pa = slot->pa[c.lane];
-            const unsigned long long cl0 = slot->cl[0][c.lane], cl1 = ZM > 4 ? slot->cl[1][c.lane] : 0ull;
-            auto firm_of = [&](int k) -> unsigned { return k < 4 ? (unsigned)(cl0 >> (16 * k)) & 0xffffu : (unsigned)(cl1 >> (16 * (k - 4))) & 0xffffu; };
             const int h = slot->h[c.lane];
-            double dk[ZM];
+            double dk[ZM]; int off[ZM];
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) dk[k] = slot->dk[k][c.lane];
+            for (int k = 0; k < ZM; ++k) { dk[k] = slot->dk[k][c.lane]; off[k] = slot->off[k][c.lane]; }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(&bars[2 * s + 1]);                   // slot may be refilled
+            if (c.lane == 0) mbar_arrive(&bars[2 * s + 1]);              // slot may be refilled
             unsigned m = __ballot_sync(FULL, b > 0.0);
             while (m) {
                 const int l = __ffs(m) - 1; m &= m - 1;
                 if (c.lane == l) {
-                    double ys[ZM], yd[ZM], q[ZM];
+                    // pull every candidate's (stock, demand) pair up front: one latency per turn
+                    double2 rec[ZM];
+#pragma unroll
+                    for (int k = 0; k < ZM; ++k) rec[k] = *reinterpret_cast<const double2 *>(mbase + off[k]);
 #pragma unroll
                     for (int k = 0; k < ZM; ++k) {
-                        if (k < z) {
-                            const MktRec *r = &mkt[firm_of(k)];
-                            double2 a0 = *reinterpret_cast<const double2 *>(r);
-                            ys[k] = a0.x; yd[k] = a0.y; q[k] = r->q;
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < ZM; ++k) {
-                        if (k < z && b > 0.0) {
-                            MktRec *r = &mkt[firm_of(k)];
+                        if (b > 0.0) {
+                            MktRec *r = reinterpret_cast<MktRec *>(mbase + off[k]);
                             const double d = dk[k];
-                            yd[k] = yd[k] + d;
-                            if (ys[k] > 0.0) {
-                                if (ys[k] > d) {
-                                    ys[k] = ys[k] - d;
-                                    q[k] = q[k] + d;
+                            double ys = rec[k].x;
+                            const double yd = rec[k].y + d;
+                            if (ys > 0.0) {
+                                if (ys > d) {
+                                    ys = ys - d;
+                                    r->q = r->q + d;
                                     b = 0.0;
                                 } else {
-                                    const double p = r->p;
-                                    b = b - ys[k] * p;
-                                    q[k] = q[k] + ys[k];
-                                    ys[k] = 0.0;
+                                    b = b - ys * r->p;
+                                    r->q = r->q + ys;
+                                    ys = 0.0;
 #pragma unroll
-                                    for (int kk = k + 1; kk < ZM; ++kk)       // rare: partial fill
-                                        if (kk < z) dk[kk] = b / mkt[firm_of(kk)].p;
+                                    for (int kk = k + 1; kk < ZM; ++kk)      // rare: partial fill
+                                        dk[kk] = b / reinterpret_cast<const MktRec *>(mbase + off[kk])->p;
                                 }
                             }
-                            *reinterpret_cast<double2 *>(r) = make_double2(ys[k], yd[k]);
-                            r->q = q[k];
+                            *reinterpret_cast<double2 *>(r) = make_double2(ys, yd);
                         }
                     }
                 }
@@ -658,6 +657,7 @@ __device__ void phase_goods_market(Ctx &c)
         }
     }
     __syncthreads();
+    c.goods_epoch += 1u;
     {
         double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q), *Ys = c.at(L.o_cYstock);
         for (int f = c.tid; f < F; f += c.nt) { MktRec r = mkt[f]; Ys[f] = r.ys; Yd[f] = r.yd; Q[f] = r.q; }
@@ -1072,11 +1072,11 @@ __global__ void __launch_bounds__(NT, MINB) cats_period_kernel(const __grid_cons
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.o_misc + 192);
 
-    c.par_full = 0u; c.par_empty = 0u;
+    c.goods_epoch = 0u;
     if (c.tid == 0) {
         mbar_init(bar, 1);
         uint64_t *ring = reinterpret_cast<uint64_t *>(smem + L.o_misc + 128);
-        for (int i = 0; i < 2 * (NT / 32 - 1); ++i) mbar_init(&ring[i], 1);
+        for (int i = 0; i < 2 * GOODS_SLOTS; ++i) mbar_init(&ring[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -1085,6 +1085,7 @@ __global__ void __launch_bounds__(NT, MINB) cats_period_kernel(const __grid_cons
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         c.b = b;
         unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
+        c.blob = blob;
         c.PA = reinterpret_cast<double *>(blob + L.o_PA);
         c.perm = reinterpret_cast<double *>(blob + L.o_perm);
         // HBM -> smem: one TMA bulk copy of the resident prefix (firm tables, employment links)
@@ -1211,8 +1212,8 @@ using namespace cats;
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
-constexpr int kThreads = 128;   // threads per economy block
-constexpr int kMinBlocks = 4;   // __launch_bounds__ hint: register budget for >= 4 resident economies / SM
+constexpr int kThreads = 64;    // threads per economy block: one market consumer warp + one producer warp
+constexpr int kMinBlocks = 8;   // __launch_bounds__ hint: register budget for >= 8 resident economies / SM
 typedef void (*KernelFn)(const KArgs);
 static KernelFn select_kernel(int max_z)
 {
@@ -1307,7 +1308,7 @@ int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byt
     };
     for (auto &e : t)
         if (!strcmp(name, e.n)) { *byte_offset = e.off; *count = e.cnt; *dtype = e.dt; return CATS_OK; }
-    return cats_field_info(W, F, N, name, byte_offset, count, dtype);
+    return fail(CATS_EINVAL, "unknown transient field '%s'", name);
 }
 
 size_t cats_tape_bytes(int W, int F, int N, int z_c, int z_k, int z_e)

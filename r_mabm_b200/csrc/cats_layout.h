@@ -2,14 +2,17 @@
 //
 // One economy = one contiguous blob in HBM (docs/MODEL.md section 2, docs/DESIGN.md "data layout"):
 //
-//   [ scal | C-firm rows | K-firm rows | Leff | Oc |  PA | perm ]
-//     `------------- resident prefix -------------'  `- household tail -'
+//   [ scal | K-firm rows | Leff | Oc |  C-firm rows | PA | perm ]
+//     `------ resident prefix -------'  `------ streamed tail -----'
 //
-// The resident prefix (firm tables, employment links: everything the matching markets touch at
-// random) is pulled into shared memory with one TMA bulk copy and pushed back with one bulk store.
-// The household tail (wealth, permanent income) is streamed from global memory / L2 once per
-// period inside the consumption-goods loop.  Keeping it out of shared memory is what lets ~6
-// economies be resident per SM instead of 3, and the step is latency-bound, so that is throughput.
+// The resident prefix (aggregates, K-firm tables, head-counts, employment links: what the labour
+// and capital-goods markets touch at random) is pulled into shared memory with one TMA bulk copy
+// and pushed back with one bulk store.  The tail is streamed from global memory / L2: C-firm rows
+// are only ever touched by "their" thread (coalesced), and the consumption-goods market works on
+// a packed per-seller record table built in shared memory when it opens; household wealth and
+// permanent income are read and written once per period inside the goods loop.  Keeping the tail
+// out of shared memory is what lets ~8 economies be resident per SM instead of 3, and the step is
+// latency-bound, so residency is throughput.
 // All section offsets are multiples of 16 bytes (bulk-copy granularity).
 #pragma once
 #include <stdint.h>
@@ -52,7 +55,7 @@ struct Layout {
     int32_t W, F, N, H;
     int32_t rowF, rowN;  // bytes of one firm f64 row
     // persisted sections (byte offsets inside the blob)
-    int32_t o_scal, o_c, o_k, o_Leff, o_Oc, resident, o_PA, o_perm, blob;
+    int32_t o_scal, o_k, o_Leff, o_Oc, resident, o_c, o_PA, o_perm, blob;
     // transients (byte offsets inside the shared-memory working set; all >= resident)
     int32_t o_Ld, o_vac, o_cFtot, o_cKdem, o_cYstock, o_cvalinv, o_kFtot, o_kYstock, workset;
     // scratch that is never dumped
@@ -68,12 +71,12 @@ inline Layout make_layout(int W, int F, int N)
     L.rowF = up16(8ll * F); L.rowN = up16(8ll * N);
     int64_t o = 0;
     L.o_scal = (int32_t)o; o += 8 * N_SCAL;
-    L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
     L.o_k = (int32_t)o; o += (int64_t)NK_FIELDS * L.rowN;
     L.o_Leff = (int32_t)o; o += up16(4ll * (F + N));
     L.o_Oc = (int32_t)o; o += up16(4ll * W);
     o = (o + 127) & ~(int64_t)127;
     L.resident = (int32_t)o;
+    L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
     L.o_PA = (int32_t)o; o += up16(8ll * L.H);
     L.o_perm = (int32_t)o; o += up16(8ll * L.H);
     o = (o + 127) & ~(int64_t)127;
@@ -89,11 +92,11 @@ inline Layout make_layout(int W, int F, int N)
     L.o_kFtot = (int32_t)o; o += L.rowN;
     L.o_kYstock = (int32_t)o; o += L.rowN;
     L.workset = (int32_t)o;
-    // scratch: fire pool (W x {worker, key}) / job seekers (W ints) / goods-market records (F x 32 B)
-    // -- used at different times
-    L.o_scr = (int32_t)o; L.scr_bytes = up16(8ll * W > 32ll * F ? 8ll * W : 32ll * F); o += L.scr_bytes;
-    // goods-market producer/consumer ring: 3 slots of 32 prepared buyers (see GoodsSlot)
-    L.o_ring = (int32_t)o; o += 3 * (32 * (8 + 8 + 8 * MAX_Z + 16 + 4));
+    // scratch: fire pool (W x {worker, key}) / job seekers (W ints) / goods-market records
+    // ((F + 1) x 32 B, the last one a dummy) -- used at different times
+    L.o_scr = (int32_t)o; L.scr_bytes = up16(8ll * W > 32ll * (F + 1) ? 8ll * W : 32ll * (F + 1)); o += L.scr_bytes;
+    // goods-market producer/consumer ring: 2 slots of 32 prepared buyers (see GoodsSlot)
+    L.o_ring = (int32_t)o; o += 2 * (32 * (8 + 8 + 8 * MAX_Z + 4 * MAX_Z + 4));
     L.o_bad = (int32_t)o; o += up16(F + N);
     L.o_red = (int32_t)o; o += 8 * 64;
     L.o_par = (int32_t)o; o += 8 * P_SLOTS;

@@ -210,13 +210,16 @@ static double u01(uint32_t hi, uint32_t lo)
     return (double)m * (1.0 / 9007199254740992.0);
 }
 
-/* z distinct indices in [0,n): partial Fisher-Yates on a virtual identity array, draw k uses
- * word k of the agent's Philox stream: j = k + mulhi32(word, n-k).                            */
+/* z <= 8 distinct indices in [0,n): partial Fisher-Yates on a virtual identity array, fed by ONE
+ * Philox block (4 words).  Draw k < 4 uses word k: j = k + mulhi32(w_k, n-k); draw k >= 4 re-uses
+ * the low half of that product (multiply-shift chain): j = k + mulhi32(lo32(w_{k-4} * (n-k+4)), n-k). */
 static void sample_distinct(const uint32_t *words, int n, int z, int32_t *out)
 {
     int jpos[MAX_Z], jval[MAX_Z];
     for (int k = 0; k < z; ++k) {
-        int j = k + (int)(((uint64_t)words[k] * (uint64_t)(uint32_t)(n - k)) >> 32);
+        uint32_t w = words[k & 3];
+        if (k >= 4) w = (uint32_t)((uint64_t)w * (uint64_t)(uint32_t)(n - (k - 4)));
+        int j = k + (int)(((uint64_t)w * (uint64_t)(uint32_t)(n - k)) >> 32);
         int v = j, vk = k;
         for (int t = 0; t < k; ++t) {
             if (jpos[t] == j) v = jval[t];
@@ -325,9 +328,8 @@ static void draw_candidates(const Econ *e, uint32_t phase, int agent, int n, int
         memcpy(out, e->tape + off + 4u * ((size_t)agent * (size_t)zz), 4u * (size_t)z);
         return;
     }
-    uint32_t w[8];
+    uint32_t w[4];
     econ_philox(e, (uint32_t)agent, phase, 0, w);
-    if (z > 4) econ_philox(e, (uint32_t)agent, phase, 1, w + 4);
     sample_distinct(w, n, z, out);
 }
 
@@ -772,12 +774,24 @@ void ph_cons_budget(Econ *e)
     }
 }
 
+/* Demand expressed at a consumption-goods seller is accumulated in 2^-40 fixed point (wrap-around
+ * uint64 add), so that the sum does not depend on the order of the visits: docs/MODEL.md 4.4.
+ * Every other quantity of the market (stock, sales, budgets) follows the visiting order exactly. */
+#define FX_ONE 1099511627776.0 /* 2^40 */
+static uint64_t fx_from(double d)
+{
+    if (!(d < 4194304.0)) return (uint64_t)1 << 62; /* saturate (also NaN, +inf: zero prices) */
+    return (uint64_t)(int64_t)llrint(d * FX_ONE); /* round to nearest even */
+}
+static double fx_to(uint64_t a) { return (double)(int64_t)a * (1.0 / FX_ONE); }
+
 /* a16 consumption_goods_market! (cats.py:394) */
 void ph_goods_market(Econ *e)
 {
     Order o; order_init(e, MKT_GOODS, e->H, &o);
     int z = e->z_c < e->F ? e->z_c : e->F;
     const double *P = e->c[C_P];
+    uint64_t *acc = (uint64_t *)xcalloc((size_t)e->F, 8);
     for (int pos = 0; pos < e->H; ++pos) {
         int h = order_at(&o, pos);
         double b = e->budget[h];
@@ -790,7 +804,7 @@ void ph_goods_market(Econ *e)
             int best = cand[k];
             double p = P[best];
             double d = b / p;
-            e->c[C_Yd][best] = e->c[C_Yd][best] + d;
+            acc[best] += fx_from(d);
             double ys = e->c_Ystock[best];
             if (ys > 0.0) {
                 if (ys > d) {
@@ -807,6 +821,8 @@ void ph_goods_market(Econ *e)
         e->PA[h] = e->PA[h] + b; /* involuntary saving */
         e->budget[h] = b;
     }
+    for (int f = 0; f < e->F; ++f) e->c[C_Yd][f] = fx_to(acc[f]);
+    free(acc);
 }
 
 /* a17 firms_accounting! (cats.py:397-398) */

@@ -157,7 +157,7 @@ struct Draws {
         if (tape) return *reinterpret_cast<const uint32_t *>(tape + t.fire_key + 4u * (uint32_t)worker);
         return philox((uint32_t)worker, PH_FIRE, 0).x;
     }
-    // z distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
+    // z <= 8 distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
     template <int ZM>
     __device__ __forceinline__ void candidates(uint32_t phase, int agent, int n, int z, int (&out)[ZM]) const
     {
@@ -171,14 +171,12 @@ struct Draws {
             for (int k = 0; k < ZM; ++k) out[k] = k < z ? src[k] : 0;
             return;
         }
+        // ONE Philox block: draw k < 4 uses word k, draw k >= 4 re-uses the low half of that product
+        const uint4 a = philox((uint32_t)agent, phase, 0);
         uint32_t w[8];
-        uint4 a = philox((uint32_t)agent, phase, 0);
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-        w[4] = w[5] = w[6] = w[7] = 0;
-        if (ZM > 4 && z > 4) {
-            uint4 b = philox((uint32_t)agent, phase, 1);
-            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        }
+#pragma unroll
+        for (int k = 4; k < 8; ++k) w[k] = w[k - 4] * (uint32_t)(n - (k - 4));
         int jpos[ZM], jval[ZM];
 #pragma unroll
         for (int k = 0; k < ZM; ++k) {
@@ -232,29 +230,43 @@ struct Order {
     }
 };
 
-// stable ascending sort of up to MAX_Z (candidate, price) pairs, register only (rank sort)
+// stable ascending sort of ZM (candidate, price) pairs by price, register only: a sorting network
+// on the total order (price, draw index) -- the same order a stable insertion sort produces.
+// Slots k >= z must hold price = +inf (they stay behind the real candidates).
 template <int ZM>
 __device__ __forceinline__ void sort_by_price(int (&cand)[ZM], double (&pr)[ZM], int z)
 {
-    int rank[ZM];
+    int idx[ZM];
 #pragma unroll
-    for (int a = 0; a < ZM; ++a) {
-        rank[a] = 0;
-#pragma unroll
-        for (int b = 0; b < ZM; ++b)
-            if (a < z && b < z && b != a)
-                rank[a] += (pr[b] < pr[a] || (pr[b] == pr[a] && b < a)) ? 1 : 0;
+    for (int k = 0; k < ZM; ++k) idx[k] = k;
+    auto cx = [&](int i, int j) {
+        const bool sw = pr[i] > pr[j] || (pr[i] == pr[j] && idx[i] > idx[j]);
+        const double pi = pr[i], pj = pr[j];
+        const int ci = cand[i], cj = cand[j], ii = idx[i], ij = idx[j];
+        pr[i] = sw ? pj : pi; pr[j] = sw ? pi : pj;
+        cand[i] = sw ? cj : ci; cand[j] = sw ? ci : cj;
+        idx[i] = sw ? ij : ii; idx[j] = sw ? ii : ij;
+    };
+    (void)z;
+    if (ZM == 2) { cx(0, 1); }
+    else if (ZM == 5) {
+        cx(0, 1); cx(3, 4); cx(2, 4); cx(2, 3); cx(1, 4); cx(0, 3); cx(0, 2); cx(1, 3); cx(1, 2);
+    } else {
+        static_assert(ZM == 2 || ZM == 5 || ZM == 8, "sorting networks exist for 2, 5 and 8 slots");
+        cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7); cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7); cx(1, 2); cx(5, 6);
+        cx(0, 4); cx(1, 5); cx(2, 6); cx(3, 7); cx(2, 4); cx(3, 5); cx(1, 2); cx(3, 4); cx(5, 6);
     }
-    int sc[ZM]; double sp[ZM];
-#pragma unroll
-    for (int r = 0; r < ZM; ++r) {
-        sc[r] = cand[r]; sp[r] = pr[r];
-#pragma unroll
-        for (int a = 0; a < ZM; ++a)
-            if (a < z && rank[a] == r) { sc[r] = cand[a]; sp[r] = pr[a]; }
-    }
-#pragma unroll
-    for (int r = 0; r < ZM; ++r) { cand[r] = sc[r]; pr[r] = sp[r]; }
+}
+
+// demand registered at a consumption-goods seller: 2^-40 fixed point, wrap-around add (MODEL.md 4.4)
+__device__ __forceinline__ unsigned long long fx_from(double d)
+{
+    if (!(d < 4194304.0)) return 1ull << 62;
+    return (unsigned long long)__double2ll_rn(d * 1099511627776.0);
+}
+__device__ __forceinline__ double fx_to(unsigned long long a)
+{
+    return (double)(long long)a * (1.0 / 1099511627776.0);
 }
 
 __device__ __forceinline__ int d2count(double x)

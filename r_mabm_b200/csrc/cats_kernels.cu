@@ -1,16 +1,23 @@
 // cats_kernels.cu -- the batched CATS economy period kernel for sm_100a and its C-ABI.
 //
-// One thread block = one economy.  The economy blob is pulled from HBM into shared memory with a
-// single TMA bulk copy (cp.async.bulk + mbarrier), advanced n_periods periods entirely on chip,
-// and pushed back with a bulk store.  Phase order is the order of Cats.step
+// One WARP = one economy (one 32-thread block per economy, ~20 resident per SM).  The resident
+// prefix of the economy blob is pulled from HBM into shared memory with a single TMA bulk copy
+// (cp.async.bulk + mbarrier), the economy is advanced n_periods periods, and the prefix is pushed
+// back with a bulk store; the tail of the blob (employment links, C-firm rows, household wealth) is
+// streamed through L2.  Phase order is the order of Cats.step
 // (/root/reference/rmabm/environments/cats.py:355-419); every rule is docs/MODEL.md.
 //
-// Parallel structure inside a block
-//   - per-firm and per-household rules: one thread per agent (strided loops)
-//   - fp64 aggregates: det_sum, one warp per sum (fixed order => batch-size invariant, bit-exact)
-//   - matching markets (job search, capital goods, consumption goods): a warp prepares 32 agents
-//     at a time in parallel (visiting order, Philox candidate draws, price sort in registers)
-//     and commits them in visiting order, so outcomes equal the sequential reference semantics.
+// Parallel structure inside a warp
+//   - per-firm rules: lane l owns firms l, l+32, l+64, ... (coalesced rows; the fixed-order fp64
+//     aggregates "det_sum" become a register partial per lane + one xor butterfly, no memory)
+//   - matching markets (job search, capital goods, consumption goods): 32 agents in visiting order
+//     are prepared in parallel (visiting order, Philox candidate draws, price sort in registers) and
+//     committed in rounds: every lane walks its candidate list against the current seller table,
+//     lanes that meet at one seller replay each other's demands in lane order (shuffles), and the
+//     longest prefix of lanes whose outcome cannot depend on an uncommitted one is committed at
+//     once.  A round ends at the first buyer that exhausts a seller; the outcome is exactly the
+//     sequential visiting-order market of the reference, including the order of every fp64 add.
+//   - no block-level barrier anywhere: a warp never waits for another warp.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -21,13 +28,6 @@
 #include "../../include/cats_b200.h"
 #include "cats_device.cuh"
 #include "cats_layout.h"
-
-#ifndef CATS_GOODS_BACKOFF
-#define CATS_GOODS_BACKOFF 1
-#endif
-#ifndef CATS_GOODS_FASTPATH
-#define CATS_GOODS_FASTPATH 1
-#endif
 
 namespace cats {
 
@@ -57,30 +57,42 @@ struct KArgs {
     long long *cycles;  // debug: [16] per-phase clock64 totals of block 0
 };
 
-// per-block view of the shared-memory working set
+// per-warp view of the working set
 struct Ctx {
     unsigned char *sm;
-    unsigned char *blob;  // this economy's blob in global memory (C-firm rows, PA, perm live there)
+    unsigned char *blob;  // this economy's blob in global memory (Oc, C-firm rows, PA, perm live there)
     const KArgs *a;
-    double *scal, *par;
-    int *Leff, *Ld, *vac, *Oc;
-    double *PA, *perm;  // household tail: GLOBAL memory (blob), not shared
-    double *red;
-    int *misc;
-    unsigned char *bad;
-    int tid, lane, warp, nwarps, nt;
-    long long b;  // economy index inside this launch
-    int last;     // last phase id to execute (stop_phase or 99)
-    unsigned goods_epoch;  // goods markets run so far by this block (mbarrier phase bookkeeping)
+    double *scal, *par;   // shared
+    int *Leff, *Ld, *vac; // shared
+    int *Oc;              // GLOBAL
+    double *PA, *perm;    // GLOBAL
+    double *mean;         // shared scratch: 8 doubles
+    int *misc;            // shared scratch ints
+    int lane;
+    unsigned lt;          // lanes below this one
+    long long b;          // economy index inside this launch
+    int last;             // last phase id to execute (stop_phase or 99)
     Draws d;
     __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + a->L.o_c + field * a->L.rowF); }  // GLOBAL
     __device__ __forceinline__ double *kf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_k + field * a->L.rowN); }
     __device__ __forceinline__ double *at(int off) const { return reinterpret_cast<double *>(sm + off); }
+    __device__ __forceinline__ int *iat(int off) const { return reinterpret_cast<int *>(sm + off); }
 };
 
-// misc int slots / red double slots
-enum { M_NSEEK = 0, M_STATUS = 1, M_NS_C = 2, M_NS_K = 3, M_NBAD = 4, M_LSUM = 5, M_POOL = 6, M_WCNT = 8 /* .. +32 */ };
-enum { R_SUM = 0, R_MEAN = 32 };
+enum { M_STATUS = 0 };
+
+__device__ __forceinline__ double bfly(double a)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a = a + __shfl_xor_sync(FULL, a, off);
+    return a;
+}
+__device__ __forceinline__ int bfly_i(int a)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(FULL, a, off);
+    return a;
+}
 
 // ---------------------------------------------------------------------------------------------
 // a8 firms_get_credit! for one firm (cats.py:376-377)
@@ -126,212 +138,263 @@ __device__ void phase_firm_decisions(Ctx &c)
     const int F = L.F, N = L.N, last = c.last;
     const double alpha = c.par[P_alpha], q_adj = c.par[P_q_adj], p_adj = c.par[P_p_adj];
     const double wb = c.scal[S_wb];
-    for (int j = c.tid; j < F + N; j += c.nt) {
-        if (j < F) {
-            const int f = j;
-            double *De = c.cf(C_De), *P = c.cf(C_P);
-            const double Yprev = c.cf(C_Y_prev)[f], Yd = c.cf(C_Yd)[f];
-            double p = P[f], de = De[f];
-            const double prevDe = de, prevP = p;
-            // phase 3: a3 firms_decide_price_quantity! (cats.py:363)
-            {
-                double stock = Yprev - Yd, avg = c.scal[S_price];
-                double u = c.d.uniform(PH_PRICE_C, f);
-                if (stock <= 0.0) {
-                    if (p >= avg) de = Yprev + (-stock) * q_adj;
-                    else { de = Yprev; p = p * (1.0 + u * p_adj); }
+    double accC = 0.0, accK = 0.0;  // det_sum partials of new credit
+    for (int f = c.lane; f < F; f += 32) {
+        double *De = c.cf(C_De), *P = c.cf(C_P);
+        const double Yprev = c.cf(C_Y_prev)[f], Yd = c.cf(C_Yd)[f];
+        double p = P[f], de = De[f];
+        const double prevDe = de, prevP = p;
+        // phase 3: a3 firms_decide_price_quantity! (cats.py:363)
+        {
+            double stock = Yprev - Yd, avg = c.scal[S_price];
+            double u = c.d.uniform(PH_PRICE_C, f);
+            if (stock <= 0.0) {
+                if (p >= avg) de = Yprev + (-stock) * q_adj;
+                else { de = Yprev; p = p * (1.0 + u * p_adj); }
+            } else {
+                if (p > avg) { de = Yprev; p = p * (1.0 - u * p_adj); }
+                else de = Yprev - stock * q_adj;
+            }
+            if (de < alpha) de = alpha;
+        }
+        // phase 5: a5 firms_decide_investment! (cats.py:366)
+        double kd = 0.0;
+        if (last >= 5) {
+            const double Iprob = c.par[P_Iprob], barX = c.par[P_barX], eta = c.par[P_eta];
+            double u = c.d.uniform(PH_INVEST, f);
+            if (u < Iprob) {
+                double K = c.cf(C_K)[f];
+                double Kdes = c.cf(C_barYK)[f] / barX;
+                double depn = ((barX * K) * eta) / Iprob;
+                kd = (Kdes - K) + depn;
+                if (!(kd > 0.0)) kd = 0.0;
+            }
+            c.at(L.s_cKdem)[f] = kd;
+        }
+        // phase 6: a6 _implement_action (cats.py:434-464 / 673-704)
+        if (last >= 6 && f < c.a->n_agents && !(c.a->flags & CATS_FLAG_BURNIN) && c.a->actions) {
+            const long long ai = c.b * c.a->n_agents + f;
+            const bool real = c.a->mask ? (c.a->mask[ai] != 0) : true;
+            if (real) {
+                double a0 = c.a->actions[2 * ai], a1 = c.a->actions[2 * ai + 1];
+                double base = (c.a->flags & CATS_FLAG_AVG_PRICE) ? c.scal[S_price] : prevP;
+                if (c.a->flags & CATS_FLAG_LOG) {
+                    de = det_exp(det_log(prevDe + 1e-8) + a0);
+                    p = det_exp(det_log(base + 1e-8) + a1);
                 } else {
-                    if (p > avg) { de = Yprev; p = p * (1.0 - u * p_adj); }
-                    else de = Yprev - stock * q_adj;
+                    de = prevDe * a0;
+                    p = base * a1;
                 }
                 if (de < alpha) de = alpha;
             }
-            // phase 5: a5 firms_decide_investment! (cats.py:366)
-            double kd = 0.0;
-            if (last >= 5) {
-                const double Iprob = c.par[P_Iprob], barX = c.par[P_barX], eta = c.par[P_eta];
-                double u = c.d.uniform(PH_INVEST, f);
-                if (u < Iprob) {
-                    double K = c.cf(C_K)[f];
-                    double Kdes = c.cf(C_barYK)[f] / barX;
-                    double depn = ((barX * K) * eta) / Iprob;
-                    kd = (Kdes - K) + depn;
-                    if (!(kd > 0.0)) kd = 0.0;
-                }
-                c.at(L.o_cKdem)[f] = kd;
+        }
+        De[f] = de; P[f] = p;
+        // phase 7: a7 firms_decide_labour! (cats.py:373)
+        if (last >= 7) {
+            double aa = ceil(de / alpha);
+            double bb = ceil((c.cf(C_K)[f] * c.par[P_k]) / alpha);
+            int Ld = d2count(aa < bb ? aa : bb);
+            int vac = 0;
+            // phase 9: a8 firms_get_credit! (cats.py:376)
+            if (last >= 9) {
+                double liq = c.cf(C_liquidity)[f];
+                double need = (wb * (double)Ld + kd * c.scal[S_price_k]) - liq;
+                double deb = c.cf(C_deb)[f], ir = c.cf(C_interest_r)[f], Ftot;
+                credit_one(c, need, c.par[P_b1], c.par[P_b2], deb, c.cf(C_A)[f], ir, Ftot, liq, Ld,
+                           c.Leff[f], vac);
+                c.cf(C_deb)[f] = deb; c.cf(C_interest_r)[f] = ir; c.at(L.s_cFtot)[f] = Ftot;
+                accC = accC + Ftot;
             }
-            // phase 6: a6 _implement_action (cats.py:434-464 / 673-704)
-            if (last >= 6 && f < c.a->n_agents && !(c.a->flags & CATS_FLAG_BURNIN) && c.a->actions) {
-                const long long ai = c.b * c.a->n_agents + f;
-                const bool real = c.a->mask ? (c.a->mask[ai] != 0) : true;
-                if (real) {
-                    double a0 = c.a->actions[2 * ai], a1 = c.a->actions[2 * ai + 1];
-                    double base = (c.a->flags & CATS_FLAG_AVG_PRICE) ? c.scal[S_price] : prevP;
-                    if (c.a->flags & CATS_FLAG_LOG) {
-                        de = det_exp(det_log(prevDe + 1e-8) + a0);
-                        p = det_exp(det_log(base + 1e-8) + a1);
-                    } else {
-                        de = prevDe * a0;
-                        p = base * a1;
-                    }
-                    if (de < alpha) de = alpha;
-                }
-            }
-            De[f] = de; P[f] = p;
-            // phase 7: a7 firms_decide_labour! (cats.py:373)
-            if (last >= 7) {
-                double aa = ceil(de / alpha);
-                double bb = ceil((c.cf(C_K)[f] * c.par[P_k]) / alpha);
-                int Ld = d2count(aa < bb ? aa : bb);
-                int vac = 0;
-                // phase 9: a8 firms_get_credit! (cats.py:376)
-                if (last >= 9) {
-                    double liq = c.cf(C_liquidity)[f];
-                    double need = (wb * (double)Ld + kd * c.scal[S_price_k]) - liq;
-                    double deb = c.cf(C_deb)[f], ir = c.cf(C_interest_r)[f], Ftot;
-                    credit_one(c, need, c.par[P_b1], c.par[P_b2], deb, c.cf(C_A)[f], ir, Ftot, liq, Ld,
-                               c.Leff[f], vac);
-                    c.cf(C_deb)[f] = deb; c.cf(C_interest_r)[f] = ir; c.at(L.o_cFtot)[f] = Ftot;
-                }
-                c.Ld[f] = Ld; c.vac[f] = vac;
-            }
-        } else {
-            const int i = j - F;
-            double *De = c.kf(K_De), *P = c.kf(K_P);
-            const double Yprev = c.kf(K_Y_prev)[i], Yd = c.kf(K_Yd)[i], avail = c.kf(K_Yavail)[i];
-            double p = P[i], de = De[i];
-            // phase 4: a4 firms_decide_price_quantity! for K-firms (cats.py:364)
-            if (last >= 4) {
-                double stock = avail - Yd, avg = c.scal[S_price_k];
-                double u = c.d.uniform(PH_PRICE_K, i);
-                if (stock <= 0.0) {
-                    if (p >= avg) de = Yprev + (-stock) * q_adj;
-                    else { de = Yprev; p = p * (1.0 + u * p_adj); }
-                } else {
-                    if (p > avg) { de = Yprev; p = p * (1.0 - u * p_adj); }
-                    else de = Yprev - stock * q_adj;
-                }
-                if (de < alpha) de = alpha;
-                De[i] = de; P[i] = p;
-            }
-            // phase 8: a7 firms_decide_labour! for K-firms (cats.py:374)
-            if (last >= 8) {
-                int Ld = d2count(ceil(de / alpha));
-                int vac = 0;
-                // phase 10: a8 firms_get_credit! for K-firms (cats.py:377)
-                if (last >= 10) {
-                    double liq = c.kf(K_liquidity)[i];
-                    double need = wb * (double)Ld - liq;
-                    double deb = c.kf(K_deb)[i], ir = c.kf(K_interest_r)[i], Ftot;
-                    credit_one(c, need, c.par[P_b_k1], c.par[P_b_k2], deb, c.kf(K_A)[i], ir, Ftot, liq, Ld,
-                               c.Leff[F + i], vac);
-                    c.kf(K_deb)[i] = deb; c.kf(K_interest_r)[i] = ir; c.at(L.o_kFtot)[i] = Ftot;
-                }
-                c.Ld[F + i] = Ld; c.vac[F + i] = vac;
-            }
+            c.Ld[f] = Ld; c.vac[f] = vac;
         }
     }
-    __syncthreads();
+    for (int i = c.lane; i < N; i += 32) {
+        double *De = c.kf(K_De), *P = c.kf(K_P);
+        const double Yprev = c.kf(K_Y_prev)[i], Yd = c.kf(K_Yd)[i], avail = c.kf(K_Yavail)[i];
+        double p = P[i], de = De[i];
+        // phase 4: a4 firms_decide_price_quantity! for K-firms (cats.py:364)
+        if (last >= 4) {
+            double stock = avail - Yd, avg = c.scal[S_price_k];
+            double u = c.d.uniform(PH_PRICE_K, i);
+            if (stock <= 0.0) {
+                if (p >= avg) de = Yprev + (-stock) * q_adj;
+                else { de = Yprev; p = p * (1.0 + u * p_adj); }
+            } else {
+                if (p > avg) { de = Yprev; p = p * (1.0 - u * p_adj); }
+                else de = Yprev - stock * q_adj;
+            }
+            if (de < alpha) de = alpha;
+            De[i] = de; P[i] = p;
+        }
+        // phase 8: a7 firms_decide_labour! for K-firms (cats.py:374)
+        if (last >= 8) {
+            int Ld = d2count(ceil(de / alpha));
+            int vac = 0;
+            // phase 10: a8 firms_get_credit! for K-firms (cats.py:377)
+            if (last >= 10) {
+                double liq = c.kf(K_liquidity)[i];
+                double need = wb * (double)Ld - liq;
+                double deb = c.kf(K_deb)[i], ir = c.kf(K_interest_r)[i], Ftot;
+                credit_one(c, need, c.par[P_b_k1], c.par[P_b_k2], deb, c.kf(K_A)[i], ir, Ftot, liq, Ld,
+                           c.Leff[F + i], vac);
+                c.kf(K_deb)[i] = deb; c.kf(K_interest_r)[i] = ir; c.at(L.s_kFtot)[i] = Ftot;
+                accK = accK + Ftot;
+            }
+            c.Ld[F + i] = Ld; c.vac[F + i] = vac;
+        }
+    }
     // bank loan stock: += det_sum(new credit), C-firms then K-firms
     if (last >= 9) {
-        for (int q = c.warp; q < 2; q += c.nwarps) {
-            const double *x = q == 0 ? c.at(L.o_cFtot) : c.at(L.o_kFtot);
-            double s = warp_det_sum(q == 0 ? F : N, c.lane, [&](int i) { return x[i]; });
-            if (c.lane == 0) c.red[R_SUM + q] = s;
-        }
-        __syncthreads();
-        if (c.tid == 0) {
-            double loans = c.scal[S_bank_loans] + c.red[R_SUM + 0];
-            if (last >= 10) loans = loans + c.red[R_SUM + 1];
+        accC = bfly(accC); accK = bfly(accK);
+        if (c.lane == 0) {
+            double loans = c.scal[S_bank_loans] + accC;
+            if (last >= 10) loans = loans + accK;
             c.scal[S_bank_loans] = loans;
         }
     }
+    __syncwarp();
 }
 
 // a9 firms_fire_workers! (cats.py:379-380).  A firm with s = Leff - Ld > 0 dismisses the s
-// employees with the smallest (fire_key, worker index).  Step 1 gathers the employees of every
-// over-staffed firm into a pool (one pass over the workers); step 2: one warp per over-staffed
-// firm does s arg-min selections over the pool.  The result does not depend on the pool order.
+// employees with the smallest (fire_key, worker index).  The employees of the over-staffed firms
+// are bucketed by firm (count, prefix, scatter) and every pooled worker ranks itself inside its
+// firm's bucket; rank < s means dismissed.  The result does not depend on the bucket order.
 __device__ void phase_fire(Ctx &c, int limit)
 {
     const Layout &L = c.a->L;
-    const int W = L.W;
-    int *pool_w = reinterpret_cast<int *>(c.sm + L.o_scr);
-    unsigned *pool_k = reinterpret_cast<unsigned *>(c.sm + L.o_scr) + W;
-    if (c.tid == 0) c.misc[M_POOL] = 0;
-    __syncthreads();
-    for (int w = c.tid; w < W; w += c.nt) {
+    const int W = L.W, lane = c.lane;
+    int *icnt = c.iat(L.s_icnt), *icur = c.iat(L.s_icur);
+    bool over = false;
+    for (int f = lane; f < limit; f += 32) { over |= c.vac[f] < 0; icnt[f] = 0; }
+    if (!__any_sync(FULL, over)) return;
+    __syncwarp();
+    for (int w = lane; w < W; w += 32) {
         int f = c.Oc[w];
-        if (f >= 0 && f < limit && c.vac[f] < 0) {
-            int i = atomicAdd(&c.misc[M_POOL], 1);
-            pool_w[i] = w; pool_k[i] = c.d.fire_key(w);
-        }
+        if (f >= 0 && f < limit && c.vac[f] < 0) atomicAdd(&icnt[f], 1);
     }
-    __syncthreads();
-    const int n = c.misc[M_POOL];
-    if (n == 0) return;
-    for (int f = c.warp; f < limit; f += c.nwarps) {
-        int s = -c.vac[f];
-        if (s <= 0) continue;
-        for (int r = 0; r < s; ++r) {
-            unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
-            for (int i = c.lane; i < n; i += 32) {
-                int w = pool_w[i];
-                if (c.Oc[w] == f) {
-                    unsigned key = pool_k[i];
-                    if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
+    __syncwarp();
+    const int cap = L.U_bytes / 8;
+    int *pool_w = c.iat(L.s_U);
+    unsigned *pool_k = reinterpret_cast<unsigned *>(c.sm + L.s_U) + cap;
+    int f0 = 0;
+    while (f0 < limit) {
+        // batch [f0, f1): consecutive firms whose pooled employees fit the pool
+        int base = 0, f1 = f0;
+        bool stop = false;
+        while (!stop && f1 < limit) {
+            const int f = f1 + lane;
+            const int n = f < limit ? icnt[f] : 0;
+            int incl = n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
+            const unsigned fm = __ballot_sync(FULL, base + incl <= cap);
+            const int nfit = fm == FULL ? 32 : __ffs(~fm) - 1;
+            if (f < limit && lane < nfit) icur[f] = base + incl - n;
+            const int add = __shfl_sync(FULL, incl, nfit > 0 ? nfit - 1 : 0);
+            if (nfit > 0) base += add;
+            f1 += nfit;
+            if (nfit < 32) stop = true;
+        }
+        if (f1 > limit) f1 = limit;
+        __syncwarp();
+        if (f1 == f0) {
+            // one firm larger than the pool: s arg-min selections over all workers (slow, rare)
+            const int f = f0;
+            const int s = -c.vac[f];
+            for (int r = 0; r < s; ++r) {
+                unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
+                for (int w = lane; w < W; w += 32) {
+                    if (c.Oc[w] == f) {
+                        unsigned key = c.d.fire_key(w);
+                        if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    unsigned ok = __shfl_xor_sync(FULL, bk, off);
+                    int ow = __shfl_xor_sync(FULL, bw, off);
+                    if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
+                }
+                if (bw == 0x7fffffff) break;
+                if (lane == 0) c.Oc[bw] = -1;
+                __syncwarp();
+            }
+            if (lane == 0) { c.Leff[f] = c.Ld[f]; c.vac[f] = 0; }
+            __syncwarp();
+            f0 = f + 1;
+            continue;
+        }
+        const int total = base;
+        if (total > 0) {
+            for (int w = lane; w < W; w += 32) {
+                int f = c.Oc[w];
+                if (f >= f0 && f < f1 && c.vac[f] < 0) {
+                    int slot = atomicAdd(&icur[f], 1);
+                    pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
                 }
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                unsigned ok = __shfl_xor_sync(FULL, bk, off);
-                int ow = __shfl_xor_sync(FULL, bw, off);
-                if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
+            __syncwarp();
+            for (int i = lane; i < total; i += 32) {
+                const int w = pool_w[i]; const unsigned key = pool_k[i];
+                const int f = c.Oc[w];
+                const int end = icur[f], beg = end - icnt[f];
+                int rank = 0;
+                for (int j = beg; j < end; ++j) {
+                    const unsigned kj = pool_k[j]; const int wj = pool_w[j];
+                    rank += (kj < key || (kj == key && wj < w)) ? 1 : 0;
+                }
+                if (rank < -c.vac[f]) c.Oc[w] = -1;
             }
-            if (bw == 0x7fffffff) break;
-            if (c.lane == 0) c.Oc[bw] = -1;
             __syncwarp();
         }
-        if (c.lane == 0) { c.Leff[f] = c.Ld[f]; c.vac[f] = 0; }
+        for (int f = f0 + lane; f < f1; f += 32)
+            if (c.vac[f] < 0) { c.Leff[f] = c.Ld[f]; c.vac[f] = 0; }
+        __syncwarp();
+        f0 = f1;
     }
 }
 
-// a10 workers_search_job! (cats.py:382).  The unemployed are compacted in visiting order; warp 0
-// then takes 32 of them at a time.  Every lane picks the first of its z_e candidates that still
-// has a vacancy; the longest prefix of lanes whose picks cannot have been pre-empted by a lower
-// lane is committed at once (lane j is safe iff fewer than vac[f] lower lanes chose the same f),
-// the rest retry against the updated vacancies.  Outcome == the sequential visiting-order rule.
+// a10 workers_search_job! (cats.py:382).  The unemployed are compacted in visiting order, then
+// taken 32 at a time.  Every lane picks the first of its z_e candidates that still has a vacancy;
+// the longest prefix of lanes whose picks cannot have been pre-empted by a lower lane is committed
+// at once (lane j is safe iff fewer than vac[f] lower lanes chose the same f), the rest retry
+// against the updated vacancies.  Outcome == the sequential visiting-order rule.
 template <int ZM>
 __device__ void phase_job_search(Ctx &c)
 {
     const Layout &L = c.a->L;
-    const int W = L.W, nf = L.F + L.N;
+    const int W = L.W, nf = L.F + L.N, lane = c.lane;
     const int z = c.d.z_e < nf ? c.d.z_e : nf;
     Order ord; ord.init(c.d, MKT_JOB, W);
-    int *seekers = reinterpret_cast<int *>(c.sm + L.o_scr);
+    int *seekers = c.iat(L.s_U);
     int total = 0;
-    for (int base = 0; base < W; base += c.nt) {
-        int pos = base + c.tid, w = -1; bool un = false;
-        if (pos < W) { w = ord.at(pos); un = c.Oc[w] < 0; }
-        unsigned bal = __ballot_sync(FULL, un);
-        if (c.lane == 0) c.misc[M_WCNT + c.warp] = __popc(bal);
-        __syncthreads();
-        int before = 0, all = 0;
-        for (int q = 0; q < c.nwarps; ++q) { int n = c.misc[M_WCNT + q]; if (q < c.warp) before += n; all += n; }
-        if (un) seekers[total + before + __popc(bal & ((1u << c.lane) - 1u))] = w;
-        total += all;
-        __syncthreads();
+    for (int base = 0; base < W; base += 128) {
+        int w[4]; int oc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pos = base + 32 * q + lane;
+            w[q] = pos < W ? ord.at(pos) : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oc[q] = w[q] >= 0 ? c.Oc[w[q]] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool un = oc[q] < 0;
+            const unsigned bal = __ballot_sync(FULL, un);
+            if (un) seekers[total + __popc(bal & c.lt)] = w[q];
+            total += __popc(bal);
+        }
     }
-    if (c.warp != 0) return;
-    const unsigned lt = (1u << c.lane) - 1u;
+    __syncwarp();
+    const unsigned lt = c.lt;
     for (int base = 0; base < total; base += 32) {
-        const int idx = base + c.lane;
+        const int idx = base + lane;
         int w = -1;
         int cand[ZM];
         if (idx < total) { w = seekers[idx]; c.d.candidates<ZM>(PH_JOB, w, nf, z, cand); }
         unsigned pending = __ballot_sync(FULL, idx < total);
         while (pending) {
-            const bool mine = (pending >> c.lane) & 1u;
+            const bool mine = (pending >> lane) & 1u;
             int pick = -1;
             if (mine) {
 #pragma unroll
@@ -339,12 +402,12 @@ __device__ void phase_job_search(Ctx &c)
                     if (k < z && pick < 0 && c.vac[cand[k]] > 0) pick = cand[k];
             }
             const bool has = mine && pick >= 0;
-            const unsigned peers = __match_any_sync(FULL, has ? pick : -1 - c.lane);
+            const unsigned peers = __match_any_sync(FULL, has ? pick : -1 - lane);
             const bool ok = !has || __popc(peers & lt) < c.vac[pick];
             const unsigned badm = __ballot_sync(FULL, mine && !ok);
             const unsigned commit = badm ? (pending & ((1u << (__ffs(badm) - 1)) - 1u)) : pending;
             __syncwarp();
-            if (has && ((commit >> c.lane) & 1u)) {
+            if (has && ((commit >> lane) & 1u)) {
                 c.Oc[w] = pick;
                 const unsigned grp = peers & commit;
                 if ((grp & lt) == 0) { int n = __popc(grp); c.vac[pick] -= n; c.Leff[pick] += n; }
@@ -355,6 +418,11 @@ __device__ void phase_job_search(Ctx &c)
     }
 }
 
+// One consumption-goods seller as the market sees it.  The SoA rows (P, Yd, Q, stock) are packed
+// into this 32-byte record when production is decided and unpacked when the market closes.
+// acc: demand expressed at the seller, 2^-40 fixed point (order-independent: MODEL.md 4.4).
+struct __align__(16) MktRec { double ys, p, q; unsigned long long acc; };
+
 // a11 firms_produce! (cats.py:384-385)
 __device__ void phase_produce(Ctx &c)
 {
@@ -362,32 +430,36 @@ __device__ void phase_produce(Ctx &c)
     const int F = L.F, N = L.N, last = c.last;
     const double alpha = c.par[P_alpha], k = c.par[P_k], eta = c.par[P_eta], theta = c.par[P_theta];
     const double wb = c.scal[S_wb], pk = c.scal[S_price_k];
-    for (int j = c.tid; j < F + N; j += c.nt) {
-        if (j < F) {
-            const int f = j;
-            double Leff = (double)c.Leff[f];
-            double cap_l = Leff * alpha, cap_k = c.cf(C_K)[f] * k;
-            double Yp = cap_l < cap_k ? cap_l : cap_k;
-            double De = c.cf(C_De)[f];
-            double Y = De < Yp ? De : Yp;
-            c.cf(C_Y_prev)[f] = Y; c.at(L.o_cYstock)[f] = Y;
-            double deb = c.cf(C_deb)[f];
-            double interests = c.cf(C_interest_r)[f] * deb;
-            double wages = wb * Leff;
-            c.cf(C_interests)[f] = interests; c.cf(C_wages)[f] = wages;
-            double Pl = 0.0;
-            if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
-            if (c.cf(C_P)[f] < Pl) c.cf(C_P)[f] = Pl;
-            c.cf(C_Q)[f] = 0.0; c.cf(C_Yd)[f] = 0.0; c.cf(C_investment)[f] = 0.0; c.at(L.o_cvalinv)[f] = 0.0;
-        } else if (last >= 15) {
-            const int i = j - F;
+    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
+    for (int f = c.lane; f < F; f += 32) {
+        double Leff = (double)c.Leff[f];
+        double cap_l = Leff * alpha, cap_k = c.cf(C_K)[f] * k;
+        double Yp = cap_l < cap_k ? cap_l : cap_k;
+        double De = c.cf(C_De)[f];
+        double Y = De < Yp ? De : Yp;
+        c.cf(C_Y_prev)[f] = Y;
+        double deb = c.cf(C_deb)[f];
+        double interests = c.cf(C_interest_r)[f] * deb;
+        double wages = wb * Leff;
+        c.cf(C_interests)[f] = interests; c.cf(C_wages)[f] = wages;
+        double Pl = 0.0;
+        if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
+        double P = c.cf(C_P)[f];
+        if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
+        MktRec r; r.ys = Y; r.p = P; r.q = 0.0; r.acc = 0ull; mkt[f] = r;
+        c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
+        if (last < 20) { c.cf(C_Q)[f] = 0.0; c.cf(C_Yd)[f] = 0.0; }   // else written when the goods market closes
+    }
+    if (c.lane == 0) { MktRec r; r.ys = 0.0; r.p = 1.0; r.q = 0.0; r.acc = 0ull; mkt[F] = r; }
+    if (last >= 15) {
+        for (int i = c.lane; i < N; i += 32) {
             double Leff = (double)c.Leff[F + i];
             double want = c.kf(K_De)[i];
             double cap_l = Leff * alpha;
             double Y = want < cap_l ? want : cap_l;
             c.kf(K_Y_prev)[i] = Y;
             double avail = Y + c.kf(K_inv)[i];
-            c.at(L.o_kYstock)[i] = avail; c.kf(K_Yavail)[i] = avail;
+            c.at(L.s_kYstock)[i] = avail; c.kf(K_Yavail)[i] = avail;
             double deb = c.kf(K_deb)[i];
             double interests = c.kf(K_interest_r)[i] * deb;
             double wages = wb * Leff;
@@ -398,56 +470,73 @@ __device__ void phase_produce(Ctx &c)
             c.kf(K_Q)[i] = 0.0; c.kf(K_Yd)[i] = 0.0;
         }
     }
+    __syncwarp();
 }
 
-// a12 capital_goods_market! (cats.py:387)
+// a12 capital_goods_market! (cats.py:387).  The investing C-firms are compacted in visiting order;
+// 32 of them at a time draw and price-sort their z_k suppliers in parallel and then trade one after
+// the other (there are ~F * Iprob buyers per period: a short chain).
 template <int ZM>
 __device__ void phase_capital_market(Ctx &c)
 {
-    if (c.warp != 0) return;
     const Layout &L = c.a->L;
-    const int F = L.F, N = L.N;
+    const int F = L.F, N = L.N, lane = c.lane;
     const int z = c.d.z_k < N ? c.d.z_k : N;
     Order ord; ord.init(c.d, MKT_CAP, F);
-    double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.o_kYstock);
-    double *Kdem = c.at(L.o_cKdem), *Ftot = c.at(L.o_cFtot), *liq = c.cf(C_liquidity);
-    double *inv = c.cf(C_investment), *valinv = c.at(L.o_cvalinv), *wages = c.cf(C_wages);
+    double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.s_kYstock);
+    double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
+    double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
+    int *buyers = c.iat(L.s_icnt);
+    int total = 0;
     for (int base = 0; base < F; base += 32) {
-        int pos = base + c.lane, f = -1; bool act = false; double kd = 0.0;
+        const int pos = base + lane;
+        int f = -1; bool act = false;
+        if (pos < F) { f = ord.at(pos); act = Kdem[f] > 0.0; }
+        const unsigned bal = __ballot_sync(FULL, act);
+        if (act) buyers[total + __popc(bal & c.lt)] = f;
+        total += __popc(bal);
+    }
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        const bool act = idx < total;
+        int f = 0; double kd = 0.0, cb = 0.0, lq = 0.0;
         int cand[ZM]; double pr[ZM];
-        if (pos < F) { f = ord.at(pos); kd = Kdem[f]; act = kd > 0.0; }
+#pragma unroll
+        for (int k = 0; k < ZM; ++k) { cand[k] = 0; pr[k] = __longlong_as_double(0x7ff0000000000000LL); }
         if (act) {
+            f = buyers[idx]; kd = Kdem[f]; lq = liq[f];
+            cb = (Ftot[f] + lq) - wages[f];
             c.d.candidates<ZM>(PH_CAP, f, N, z, cand);
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) pr[k] = k < z ? Pk[cand[k]] : 0.0;
+            for (int k = 0; k < ZM; ++k) if (k < z) pr[k] = Pk[cand[k]];
             sort_by_price<ZM>(cand, pr, z);
         }
         unsigned m = __ballot_sync(FULL, act);
         while (m) {
-            int l = __ffs(m) - 1; m &= m - 1;
-            if (c.lane == l) {
-                double cb = (Ftot[f] + liq[f]) - wages[f];
-                double lq = liq[f], iv = inv[f], vi = valinv[f];
+            const int l = __ffs(m) - 1; m &= m - 1;
+            if (lane == l) {
+                double iv = 0.0, vi = 0.0;   // produce zeroed investment and its value this period
 #pragma unroll
                 for (int k = 0; k < ZM; ++k) {
                     if (k < z && cb > 0.0 && kd > 0.0) {
-                        int best = cand[k];
-                        double pk = pr[k];
-                        double afford = cb / pk;
-                        double want = afford < kd ? afford : kd;
+                        const int best = cand[k];
+                        const double pk = pr[k];
+                        const double afford = cb / pk;
+                        const double want = afford < kd ? afford : kd;
                         Ydk[best] = Ydk[best] + want;
-                        double ys = Ysk[best];
+                        const double ys = Ysk[best];
                         if (ys > 0.0) {
-                            double full = kd * pk;
-                            double spend = cb < full ? cb : full;
-                            double q = spend / pk;
+                            const double full = kd * pk;
+                            const double spend = cb < full ? cb : full;
+                            const double q = spend / pk;
                             if (ys > q) {
                                 Ysk[best] = ys - q;
                                 Qk[best] = Qk[best] + q;
                                 kd = kd - q; cb = cb - spend;
                                 lq = lq - spend; iv = iv + q; vi = vi + spend;
                             } else {
-                                double cost = ys * pk;
+                                const double cost = ys * pk;
                                 kd = kd - ys; cb = cb - cost;
                                 lq = lq - cost;
                                 Qk[best] = Qk[best] + ys;
@@ -462,6 +551,7 @@ __device__ void phase_capital_market(Ctx &c)
             __syncwarp();
         }
     }
+    __syncwarp();
 }
 
 // a13 gov_adjusts_subsidy! (cats.py:389) and the government side of a14 workers_get_paid!
@@ -470,248 +560,246 @@ __device__ void phase_capital_market(Ctx &c)
 __device__ void phase_gov_income(Ctx &c)
 {
     const Layout &L = c.a->L;
-    if (c.warp == 0) {
-        int n = warp_int_sum(L.F + L.N, c.lane, [&](int i) { return c.Leff[i]; });
-        if (c.lane == 0) {
-            double sub = c.par[P_subsidy] * c.scal[S_wb];
-            if (c.par[P_maastricht] > 0.0 && c.scal[S_deficitGDP] > c.par[P_target_deficit]) {
-                double scale = 1.0 - c.par[P_maastricht] * (c.scal[S_deficitGDP] - c.par[P_target_deficit]);
-                if (!(scale > 0.0)) scale = 0.0;
-                sub = sub * scale;
-            }
-            c.scal[S_gov_subsidy_level] = sub;
-            if (c.last >= 18) {
-                const double wb = c.scal[S_wb], tax = c.par[P_tax_rate];
-                c.scal[S_gov_TA] = c.scal[S_gov_TA] + (wb * tax) * (double)n;
-                c.scal[S_gov_G] = c.scal[S_gov_G] + sub * (double)(L.W - n);
-            }
+    int n = 0;
+    for (int i = c.lane; i < L.F + L.N; i += 32) n += c.Leff[i];
+    n = bfly_i(n);
+    if (c.lane == 0) {
+        double sub = c.par[P_subsidy] * c.scal[S_wb];
+        if (c.par[P_maastricht] > 0.0 && c.scal[S_deficitGDP] > c.par[P_target_deficit]) {
+            double scale = 1.0 - c.par[P_maastricht] * (c.scal[S_deficitGDP] - c.par[P_target_deficit]);
+            if (!(scale > 0.0)) scale = 0.0;
+            sub = sub * scale;
+        }
+        c.scal[S_gov_subsidy_level] = sub;
+        if (c.last >= 18) {
+            const double wb = c.scal[S_wb], tax = c.par[P_tax_rate];
+            c.scal[S_gov_TA] = c.scal[S_gov_TA] + (wb * tax) * (double)n;
+            c.scal[S_gov_G] = c.scal[S_gov_G] + sub * (double)(L.W - n);
         }
     }
-}
-
-// income and consumption budget of one household (a14 workers_get_paid!, a15
-// households_find_cons_budget!, cats.py:391-393); pa/pm are updated in place, returns the budget
-__device__ __forceinline__ double household_budget(const Ctx &c, int h, double &pa, double &pm, int upto)
-{
-    const Layout &L = c.a->L;
-    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
-    double inc;
-    if (h < L.W) {
-        inc = c.Oc[h] >= 0 ? wb * (1.0 - c.par[P_tax_rate]) : sub;
-        pa = pa + inc;
-    } else {
-        inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
-    }
-    if (upto < 19) return 0.0;
-    const double xi = c.par[P_xi], chi = c.par[P_chi];
-    double ir = inc / price;
-    pm = pm * xi + (1.0 - xi) * ir;
-    double target = pm + (chi * pa) / price;
-    double b = target * price;
-    if (b > pa) b = pa;
-    if (!(b > 0.0)) b = 0.0;
-    pa = pa - b;
-    return b;
+    __syncwarp();
 }
 
 // debug path only (stop_phase 18 / 19): the household rules without the market
 __device__ void phase_households_only(Ctx &c)
 {
-    for (int h = c.tid; h < c.a->L.H; h += c.nt) {
+    const Layout &L = c.a->L;
+    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
+    const double xi = c.par[P_xi], chi = c.par[P_chi];
+    for (int h = c.lane; h < L.H; h += 32) {
         double pa = c.PA[h], pm = c.perm[h];
-        household_budget(c, h, pa, pm, c.last);
+        double inc;
+        if (h < L.W) { inc = c.Oc[h] >= 0 ? wb * (1.0 - c.par[P_tax_rate]) : sub; pa = pa + inc; }
+        else inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
+        if (c.last >= 19) {
+            double ir = inc / price;
+            pm = pm * xi + (1.0 - xi) * ir;
+            double target = pm + (chi * pa) / price;
+            double b = target * price;
+            if (b > pa) b = pa;
+            if (!(b > 0.0)) b = 0.0;
+            pa = pa - b;
+        }
         c.PA[h] = pa; c.perm[h] = pm;
     }
+    __syncwarp();
 }
 
-// One consumption-goods seller as the market sees it.  The SoA rows (P, Yd, Q, stock) are packed
-// into this 32-byte record when the market opens and unpacked when it closes, so that a visit is
-// one shared-memory round trip instead of three dependent ones.
-struct __align__(16) MktRec { double ys, yd, q, p; };
-
-// a14 + a15 + a16 consumption_goods_market! (cats.py:391-394), fused and warp-specialised.
-//
-// Households are visited in the market's random order, 32 ("a chunk") at a time.
-//   producers (warps 1..): for one chunk each, every lane pulls its household's wealth and
-//       permanent income from global memory, computes income and budget (a14, a15), draws the z_c
-//       candidate firms (Philox), sorts them by price and pre-divides the demand b/P it would
-//       express at each -- then publishes the chunk in a shared-memory slot (mbarrier "full").
-//   consumer (warp 0): takes the chunks in order and lets the lanes commit one after the other in
-//       visiting order against the sellers' records -- the sequential-market rule of the reference.
-//       All candidate records of a buyer are pulled up front, so a turn is one smem round trip.
-// The serial chain is what bounds an economy-period; the producers keep everything that does not
-// depend on market state off it.
-struct GoodsSlot {            // one chunk of 32 prepared buyers, SoA over lanes
-    double b[32];             // budget
-    double pa[32];            // wealth after the budget was set aside
-    double dk[MAX_Z][32];     // demand b / P at the k-th cheapest candidate
-    int off[MAX_Z][32];       // shared-memory byte offset of the k-th candidate's MktRec (dummy record if k >= z)
-    int h[32];                // household id (-1: no household in this lane)
-};
-static_assert(sizeof(GoodsSlot) == 32 * (8 + 8 + 8 * MAX_Z + 4 * MAX_Z + 4), "GoodsSlot must match cats_layout.h o_ring sizing");
-constexpr int GOODS_SLOTS = 2;
-
+// a14 + a15 + a16: workers_get_paid!, households_find_cons_budget!, consumption_goods_market!
+// (cats.py:391-394), fused.  Households are visited in the market's random order, 32 at a time.
+//   prepare (lane-parallel): gather wealth / permanent income / employment link (prefetched one
+//       chunk ahead), income and budget, z_c Philox candidates, price sort.
+//   commit (rounds): every "dirty" lane walks down its sorted candidates: at each seller it
+//       registers its demand b / P (fixed-point atomic add: order-free) and stops at the first one
+//       with stock, its terminal.  Lanes with the same terminal replay the purchases of the lower
+//       lanes in lane order (shuffles), so each knows the stock it will find.  Everything up to and
+//       including the first lane that exhausts its seller is committed; that lane (with what is left
+//       of its budget) and the lanes queued behind it at the exhausted seller walk on in the next
+//       round.  Stock, sales and budgets therefore follow the visiting order exactly.
 template <int ZM>
 __device__ void phase_goods_market(Ctx &c)
 {
     const Layout &L = c.a->L;
-    const int F = L.F, H = L.H;
+    const int W = L.W, F = L.F, H = L.H, lane = c.lane;
+    const unsigned lt = c.lt;
     const int z = c.d.z_c < F ? c.d.z_c : F;
-    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.o_scr);   // F records + 1 dummy
-    {
-        const double *P = c.cf(C_P), *Ys = c.at(L.o_cYstock);
-        for (int f = c.tid; f <= F; f += c.nt) {
-            MktRec r; r.ys = f < F ? Ys[f] : 0.0; r.yd = 0.0; r.q = 0.0; r.p = f < F ? P[f] : 1.0; mkt[f] = r;
+    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
+    Order ord; ord.init(c.d, MKT_GOODS, H);
+    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
+    const double xi = c.par[P_xi], chi = c.par[P_chi];
+    const double net = wb * (1.0 - c.par[P_tax_rate]);
+    const double ir_emp = net / price, ir_un = sub / price;
+    const double omxi = 1.0 - xi;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int nch = (H + 31) / 32;
+
+    // one chunk of households ahead: id, wealth, permanent income, employment link / dividend
+    int h_n = -1, oc_n = -1; double pa_n = 0.0, pm_n = 0.0, dinc_n = 0.0;
+    auto fetch = [&](int ch) {
+        const int pos = ch * 32 + lane;
+        h_n = -1; oc_n = -1; pa_n = 0.0; pm_n = 0.0; dinc_n = 0.0;
+        if (pos < H) {
+            const int h = ord.at(pos);
+            h_n = h; pa_n = c.PA[h]; pm_n = c.perm[h];
+            if (h < W) oc_n = c.Oc[h];
+            else if (h < W + F) dinc_n = c.cf(C_div_income)[h - W];
+            else dinc_n = c.kf(K_div_income)[h - W - F];
         }
-    }
-    __syncthreads();
-    const int nchunks = (H + 31) / 32;
-    const int nprod = c.nwarps - 1;
-    unsigned char *slots = c.sm + L.o_ring;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(c.sm + L.o_misc + 128);  // full[s] = bars[2s], empty[s] = bars[2s+1]
-    if (c.warp > 0) {
-        // ---------------- producers: chunk ch goes to slot ch % GOODS_SLOTS, made by warp 1 + ch % nprod
-        Order ord; ord.init(c.d, MKT_GOODS, H);
-        for (int ch = c.warp - 1; ch < nchunks; ch += nprod) {
-            const int s = ch % GOODS_SLOTS;
-            GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
-            const int pos = ch * 32 + c.lane;
-            int h = -1; double pa = 0.0, pm = 0.0, b = 0.0;
-            int cand[ZM]; double pr[ZM], dk[ZM];
-#pragma unroll
-            for (int k = 0; k < ZM; ++k) { dk[k] = 0.0; cand[k] = F; }
-            if (pos < H) {
-                h = ord.at(pos);
-                pa = c.PA[h]; pm = c.perm[h];
-                b = household_budget(c, h, pa, pm, 99);
-                c.perm[h] = pm;
-            }
-            if (b > 0.0) {
-                c.d.candidates<ZM>(PH_GOODS, h, F, z, cand);
-#pragma unroll
-                for (int k = 0; k < ZM; ++k) pr[k] = k < z ? mkt[cand[k]].p : 1.0;
-                sort_by_price<ZM>(cand, pr, z);
-#pragma unroll
-                for (int k = 0; k < ZM; ++k) { dk[k] = k < z ? b / pr[k] : 0.0; if (k >= z) cand[k] = F; }
-            }
-            // wait until the consumer has drained the previous occupant of this slot
-            const unsigned use = c.goods_epoch * (unsigned)((nchunks + GOODS_SLOTS - 1 - s) / GOODS_SLOTS) + (unsigned)(ch / GOODS_SLOTS);  // n-th use of the slot since kernel start
-            mbar_wait_backoff(&bars[2 * s + 1], (use & 1u) ^ 1u);
-            slot->b[c.lane] = b; slot->pa[c.lane] = pa; slot->h[c.lane] = h;
-#pragma unroll
-            for (int k = 0; k < ZM; ++k) { slot->dk[k][c.lane] = dk[k]; slot->off[k][c.lane] = cand[k] * (int)sizeof(MktRec); }
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&bars[2 * s]);                  // publish
+    };
+    fetch(0);
+    for (int ch = 0; ch < nch; ++ch) {
+        const int h = h_n, oc = oc_n;
+        double pa = pa_n, pm = pm_n;
+        const double dinc = dinc_n;
+        if (ch + 1 < nch) fetch(ch + 1);
+        // a14 + a15: income, permanent income, consumption budget
+        double b = 0.0;
+        if (h >= 0) {
+            double ir;
+            if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? net : sub); ir = emp ? ir_emp : ir_un; }
+            else ir = dinc / price;
+            pm = pm * xi + omxi * ir;
+            const double target = pm + (chi * pa) / price;
+            b = target * price;
+            if (b > pa) b = pa;
+            if (!(b > 0.0)) b = 0.0;
+            pa = pa - b;
+            c.perm[h] = pm;
         }
-    } else {
-        // ---------------- consumer ----------------
-        unsigned char *mbase = reinterpret_cast<unsigned char *>(mkt);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % GOODS_SLOTS;
-            GoodsSlot *slot = reinterpret_cast<GoodsSlot *>(slots + (size_t)s * sizeof(GoodsSlot));
-            mbar_wait(&bars[2 * s], (c.goods_epoch * (unsigned)((nchunks + GOODS_SLOTS - 1 - s) / GOODS_SLOTS) + (unsigned)(ch / GOODS_SLOTS)) & 1u);
-            double b = slot->b[c.lane];
-            const double pa = slot->pa[c.lane];
-            const int h = slot->h[c.lane];
-            double dk[ZM]; int off[ZM];
+        // a16: candidates, sorted by price, packed 16 bits each
+        unsigned long long cp0 = 0ull, cp1 = 0ull;
+        unsigned pend = __ballot_sync(FULL, b > 0.0);
+        if (b > 0.0) {
+            int cand[ZM]; double pr[ZM];
+            c.d.candidates<ZM>(PH_GOODS, h, F, z, cand);
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) { dk[k] = slot->dk[k][c.lane]; off[k] = slot->off[k][c.lane]; }
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&bars[2 * s + 1]);              // slot may be refilled
-            unsigned m = __ballot_sync(FULL, b > 0.0);
-            while (m) {
-                const int l = __ffs(m) - 1; m &= m - 1;
-                if (c.lane == l) {
-                    // pull every candidate's (stock, demand) pair up front: one latency per turn
-                    double2 rec[ZM];
+            for (int k = 0; k < ZM; ++k) pr[k] = k < z ? mkt[cand[k]].p : INF;
+            sort_by_price<ZM>(cand, pr, z);
 #pragma unroll
-                    for (int k = 0; k < ZM; ++k) rec[k] = *reinterpret_cast<const double2 *>(mbase + off[k]);
-#pragma unroll
-                    for (int k = 0; k < ZM; ++k) {
-                        if (b > 0.0) {
-                            MktRec *r = reinterpret_cast<MktRec *>(mbase + off[k]);
-                            const double d = dk[k];
-                            double ys = rec[k].x;
-                            const double yd = rec[k].y + d;
-                            if (ys > 0.0) {
-                                if (ys > d) {
-                                    ys = ys - d;
-                                    r->q = r->q + d;
-                                    b = 0.0;
-                                } else {
-                                    b = b - ys * r->p;
-                                    r->q = r->q + ys;
-                                    ys = 0.0;
-#pragma unroll
-                                    for (int kk = k + 1; kk < ZM; ++kk)      // rare: partial fill
-                                        dk[kk] = b / reinterpret_cast<const MktRec *>(mbase + off[kk])->p;
-                                }
-                            }
-                            *reinterpret_cast<double2 *>(r) = make_double2(ys, yd);
-                        }
+            for (int k = 0; k < ZM; ++k) {
+                if (k < 4) cp0 |= (unsigned long long)(unsigned)cand[k] << (16 * k);
+                else cp1 |= (unsigned long long)(unsigned)cand[k] << (16 * (k - 4));
+            }
+        }
+        int nrem = b > 0.0 ? z : 0, term = -1;
+        double p_t = 1.0, d_t = 0.0;
+        bool dirty = b > 0.0;
+        while (pend) {
+            // ---- walk: dirty lanes register demand seller by seller until one has stock
+            while (__any_sync(FULL, dirty)) {
+                if (dirty) {
+                    if (nrem == 0) { term = -1; dirty = false; }   // every candidate is sold out
+                    else {
+                        const int cnd = (int)(cp0 & 0xffffull);
+                        cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
+                        MktRec *r = &mkt[cnd];
+                        const double2 yp = *reinterpret_cast<const double2 *>(r);   // stock, price
+                        const double d = b / yp.y;
+                        atomicAdd(&r->acc, fx_from(d));
+                        if (yp.x > 0.0) { term = cnd; p_t = yp.y; d_t = d; dirty = false; }
                     }
                 }
-                __syncwarp();
             }
-            if (h >= 0) c.PA[h] = pa + b;
+            // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
+            const bool mine = (pend >> lane) & 1u;
+            const bool has = mine && term >= 0;
+            const unsigned peers = __match_any_sync(FULL, has ? term : -1 - lane);
+            unsigned rem = has ? (peers & lt) : 0u;
+            double ys = 0.0, q = 0.0;
+            if (has) { ys = mkt[term].ys; q = mkt[term].q; }
+            bool sold = false;
+            while (__any_sync(FULL, rem != 0u)) {
+                const int src = rem ? __ffs(rem) - 1 : 0;
+                const double di = __shfl_sync(FULL, d_t, src);
+                if (rem) {
+                    if (!sold) { if (ys > di) { ys = ys - di; q = q + di; } else sold = true; }
+                    rem &= rem - 1;
+                }
+            }
+            const bool full = has && !sold && ys > d_t;
+            const unsigned so = __ballot_sync(FULL, has && !sold && !full);   // lanes that exhaust their seller
+            const int s = so ? __ffs(so) - 1 : 31;
+            const unsigned commit = pend & (s >= 31 ? FULL : ((2u << s) - 1u));
+            const bool cm = (commit >> lane) & 1u;
+            const int xs = __shfl_sync(FULL, term, s);   // the seller exhausted by lane s (if so != 0)
+            bool done = false;
+            if (cm) {
+                if (!has) done = true;                    // nothing left to visit: the rest of b is saved
+                else {
+                    const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
+                    MktRec *r = &mkt[term];
+                    if (full) { ys = ys - d_t; q = q + d_t; b = 0.0; done = true; }
+                    else {                                 // lane s: partial fill, then walk on
+                        b = b - ys * p_t; q = q + ys; ys = 0.0;
+                        term = -1;
+                        dirty = b > 0.0;
+                        done = !dirty;
+                    }
+                    if (lastp) { r->ys = ys; r->q = q; }
+                }
+            } else if (mine && so && has && term == xs) {
+                term = -1; dirty = true;                   // queued behind lane s at the exhausted seller
+            }
+            pend &= ~__ballot_sync(FULL, done);
+            __syncwarp();
         }
+        if (h >= 0) c.PA[h] = pa + b;   // involuntary saving
     }
-    __syncthreads();
-    c.goods_epoch += 1u;
+    // close: unpack the seller records
     {
-        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q), *Ys = c.at(L.o_cYstock);
-        for (int f = c.tid; f < F; f += c.nt) { MktRec r = mkt[f]; Ys[f] = r.ys; Yd[f] = r.yd; Q[f] = r.q; }
+        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
+        for (int f = lane; f < F; f += 32) { const MktRec r = mkt[f]; Yd[f] = fx_to(r.acc); Q[f] = r.q; }
     }
+    __syncwarp();
 }
 
-// a17 firms_accounting! (cats.py:397-398) + a18 reward (cats.py:493-556)
+// a17 firms_accounting! (cats.py:397-398)
 __device__ void phase_accounting(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int W = L.W, F = L.F, N = L.N, last = c.last;
     const double delta = c.par[P_delta], eta = c.par[P_eta], k = c.par[P_k], theta = c.par[P_theta];
     const double divs = c.par[P_div], taxd = c.par[P_tax_rate_d];
-    double *inst_c = c.at(L.o_cFtot), *dtax_c = c.at(L.o_cKdem);    // rows reused once consumed
-    double *inst_k = c.at(L.o_kFtot), *dtax_k = c.at(L.o_kYstock);
-    for (int j = c.tid; j < F + N; j += c.nt) {
-        if (j < F) {
-            const int f = j;
-            double Yp = c.cf(C_Y_prev)[f];
-            c.cf(C_barYK)[f] = delta * c.cf(C_barYK)[f] + (1.0 - delta) * (Yp / k);
-            double dep = (eta * Yp) / k;
-            double Kold = c.cf(C_K)[f];
-            c.cf(C_K)[f] = (Kold - dep) + c.cf(C_investment)[f];
-            double dv = 0.0;
-            double cv = c.cf(C_capital_value)[f];
-            if (Kold != 0.0) dv = (dep * cv) / Kold;
-            c.cf(C_capital_value)[f] = (cv - dv) + c.at(L.o_cvalinv)[f];
-            double RIC = c.cf(C_P)[f] * c.cf(C_Q)[f];
-            double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f];
-            double deb = c.cf(C_deb)[f];
-            double in = theta * deb;
-            double liq = ((((c.cf(C_liquidity)[f] + RIC) + c.at(L.o_cFtot)[f]) - wages) - interests) - in;
-            c.cf(C_deb)[f] = deb - in;
-            double pi = ((RIC - wages) - interests) - dv;
-            double A = c.cf(C_A)[f] + pi;
-            double net = 0.0, dt = 0.0;
-            if (pi > 0.0) {
-                double dvd = divs * pi;
-                liq = liq - dvd; A = A - dvd;
-                net = dvd * (1.0 - taxd);
-                dt = dvd - net;
-                c.PA[W + f] = c.PA[W + f] + net;
-            }
-            c.cf(C_div_income)[f] = net;
-            c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;
-            inst_c[f] = in; dtax_c[f] = dt;
-        } else if (last >= 22) {
-            const int i = j - F;
+    const MktRec *mkt = reinterpret_cast<const MktRec *>(c.sm + L.s_U);
+    double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;   // det_sum partials
+    for (int f = c.lane; f < F; f += 32) {
+        double Yp = c.cf(C_Y_prev)[f];
+        c.cf(C_barYK)[f] = delta * c.cf(C_barYK)[f] + (1.0 - delta) * (Yp / k);
+        double dep = (eta * Yp) / k;
+        double Kold = c.cf(C_K)[f];
+        c.cf(C_K)[f] = (Kold - dep) + c.cf(C_investment)[f];
+        double dv = 0.0;
+        double cv = c.cf(C_capital_value)[f];
+        if (Kold != 0.0) dv = (dep * cv) / Kold;
+        c.cf(C_capital_value)[f] = (cv - dv) + c.at(L.s_cvalinv)[f];
+        double RIC = mkt[f].p * mkt[f].q;
+        double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f];
+        double deb = c.cf(C_deb)[f];
+        double in = theta * deb;
+        double liq = ((((c.cf(C_liquidity)[f] + RIC) + c.at(L.s_cFtot)[f]) - wages) - interests) - in;
+        c.cf(C_deb)[f] = deb - in;
+        double pi = ((RIC - wages) - interests) - dv;
+        double A = c.cf(C_A)[f] + pi;
+        double net = 0.0, dt = 0.0;
+        if (pi > 0.0) {
+            double dvd = divs * pi;
+            liq = liq - dvd; A = A - dvd;
+            net = dvd * (1.0 - taxd);
+            dt = dvd - net;
+            c.PA[W + f] = c.PA[W + f] + net;
+        }
+        c.cf(C_div_income)[f] = net;
+        c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;
+        s_in = s_in + in; s_int = s_int + interests; s_dt = s_dt + dt;
+    }
+    if (last >= 22) {
+        for (int i = c.lane; i < N; i += 32) {
             double RIC = c.kf(K_P)[i] * c.kf(K_Q)[i];
-            c.kf(K_inv)[i] = (1.0 - c.par[P_inventory_depreciation]) * c.at(L.o_kYstock)[i];
+            c.kf(K_inv)[i] = (1.0 - c.par[P_inventory_depreciation]) * c.at(L.s_kYstock)[i];
             double wages = c.kf(K_wages)[i], interests = c.kf(K_interests)[i];
             double deb = c.kf(K_deb)[i];
             double in = theta * deb;
-            double liq = ((((c.kf(K_liquidity)[i] + RIC) + c.at(L.o_kFtot)[i]) - wages) - interests) - in;
+            double liq = ((((c.kf(K_liquidity)[i] + RIC) + c.at(L.s_kFtot)[i]) - wages) - interests) - in;
             c.kf(K_deb)[i] = deb - in;
             double pi = (RIC - wages) - interests;
             double A = c.kf(K_A)[i] + pi;
@@ -725,32 +813,23 @@ __device__ void phase_accounting(Ctx &c)
             }
             c.kf(K_div_income)[i] = net;
             c.kf(K_liquidity)[i] = liq; c.kf(K_A)[i] = A;
-            inst_k[i] = in; dtax_k[i] = dt;
+            k_in = k_in + in; k_int = k_int + interests; k_dt = k_dt + dt;
         }
     }
-    __syncthreads();
     // six det_sums: installments, interests, dividend tax for C then K
-    for (int q = c.warp; q < 6; q += c.nwarps) {
-        const bool isk = q >= 3; const int n = isk ? N : F;
-        const double *x = q == 0 ? inst_c : q == 1 ? c.cf(C_interests) : q == 2 ? dtax_c
-                        : q == 3 ? inst_k : q == 4 ? c.kf(K_interests) : dtax_k;
-        double s = warp_det_sum(n, c.lane, [&](int i) { return x[i]; });
-        if (c.lane == 0) c.red[R_SUM + q] = s;
-    }
-    __syncthreads();
-    if (c.tid == 0) {
-        double loans = c.scal[S_bank_loans] - c.red[R_SUM + 0];
-        double ii = c.scal[S_bank_interest_income] + c.red[R_SUM + 1];
-        double ta = c.scal[S_gov_TA] + c.red[R_SUM + 2];
-        if (last >= 22) {
-            loans = loans - c.red[R_SUM + 3];
-            ii = ii + c.red[R_SUM + 4];
-            ta = ta + c.red[R_SUM + 5];
-        }
+    s_in = bfly(s_in); s_int = bfly(s_int); s_dt = bfly(s_dt);
+    k_in = bfly(k_in); k_int = bfly(k_int); k_dt = bfly(k_dt);
+    if (c.lane == 0) {
+        double loans = c.scal[S_bank_loans] - s_in;
+        double ii = c.scal[S_bank_interest_income] + s_int;
+        double ta = c.scal[S_gov_TA] + s_dt;
+        if (last >= 22) { loans = loans - k_in; ii = ii + k_int; ta = ta + k_dt; }
         c.scal[S_bank_loans] = loans; c.scal[S_bank_interest_income] = ii; c.scal[S_gov_TA] = ta;
     }
+    __syncwarp();
 }
 
+// a18 Cats._get_reward (cats.py:493-556), evaluated between accounting and tracking
 __device__ void phase_reward(Ctx &c)
 {
     const KArgs &a = *c.a;
@@ -759,19 +838,19 @@ __device__ void phase_reward(Ctx &c)
     const double *P = c.cf(C_P), *Q = c.cf(C_Q);
     if (a.flags & CATS_FLAG_REWARD_RMS) {
         // cats.py:548-549: Python sum() over the RL firms, then over the others, left to right
-        if (c.tid == 0) {
+        double total = 0.0;
+        if (c.lane == 0) {
             double tot_rl = 0.0, tot_other = 0.0;
             for (int f = 0; f < nA; ++f) tot_rl = tot_rl + P[f] * Q[f];
             for (int f = nA; f < F; ++f) tot_other = tot_other + P[f] * Q[f];
-            c.red[R_SUM + 8] = tot_rl + tot_other;
+            total = tot_rl + tot_other;
         }
-        __syncthreads();
-        double total = c.red[R_SUM + 8];
-        for (int i = c.tid; i < nA; i += c.nt) a.reward[c.b * nA + i] = (P[i] * Q[i]) / total;
+        total = __shfl_sync(FULL, total, 0);
+        for (int i = c.lane; i < nA; i += 32) a.reward[c.b * nA + i] = (P[i] * Q[i]) / total;
         return;
     }
     const double eta = c.par[P_eta], k = c.par[P_k];
-    for (int i = c.tid; i < nA; i += c.nt) {
+    for (int i = c.lane; i < nA; i += 32) {
         double dep = (eta * c.cf(C_Y_prev)[i]) / k;
         double den = (c.cf(C_K)[i] + dep) - c.cf(C_investment)[i];
         double dv;
@@ -784,6 +863,7 @@ __device__ void phase_reward(Ctx &c)
         if (c.cf(C_A)[i] <= 0.0) profits = a.bankruptcy_reward;
         a.reward[c.b * nA + i] = profits;
     }
+    __syncwarp();
 }
 
 // a19 update_tracking_variables! (cats.py:401)
@@ -791,33 +871,26 @@ __device__ void phase_tracking(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int F = L.F, N = L.N;
-    const double *cP = c.cf(C_P), *cQ = c.cf(C_Q), *kP = c.kf(K_P), *kQ = c.kf(K_Q);
-    for (int q = c.warp; q < 9; q += c.nwarps) {
-        if (q == 8) {
-            int n = warp_int_sum(F + N, c.lane, [&](int i) { return c.Leff[i]; });
-            if (c.lane == 0) c.misc[M_LSUM] = n;
-            continue;
-        }
-        double s;
-        switch (q) {
-        case 0: s = warp_det_sum(F, c.lane, [&](int i) { return cQ[i]; }); break;
-        case 1: s = warp_det_sum(F, c.lane, [&](int i) { return cP[i] * cQ[i]; }); break;
-        case 2: s = warp_det_sum(F, c.lane, [&](int i) { return cP[i]; }); break;
-        case 3: s = warp_det_sum(N, c.lane, [&](int i) { return kQ[i]; }); break;
-        case 4: s = warp_det_sum(N, c.lane, [&](int i) { return kP[i] * kQ[i]; }); break;
-        case 5: { const double *x = c.cf(C_Y_prev); s = warp_det_sum(F, c.lane, [&](int i) { return x[i]; }); } break;
-        case 6: { const double *x = c.kf(K_Y_prev); s = warp_det_sum(N, c.lane, [&](int i) { return x[i]; }); } break;
-        default: { const double *x = c.cf(C_K); s = warp_det_sum(F, c.lane, [&](int i) { return x[i]; }); } break;
-        }
-        if (c.lane == 0) c.red[R_SUM + q] = s;
+    const double *cP = c.cf(C_P), *cQ = c.cf(C_Q), *cY = c.cf(C_Y_prev), *cK = c.cf(C_K);
+    double sQ = 0.0, sPQ = 0.0, sP = 0.0, sY = 0.0, sK = 0.0, sQk = 0.0, sPQk = 0.0, sYk = 0.0;
+    int nL = 0;
+    for (int f = c.lane; f < F; f += 32) {
+        const double p = cP[f], q = cQ[f];
+        sQ = sQ + q; sPQ = sPQ + p * q; sP = sP + p; sY = sY + cY[f]; sK = sK + cK[f];
+        nL += c.Leff[f];
     }
-    __syncthreads();
-    if (c.tid == 0) {
-        const double *r = c.red + R_SUM;
+    for (int i = c.lane; i < N; i += 32) {
+        const double p = c.kf(K_P)[i], q = c.kf(K_Q)[i];
+        sQk = sQk + q; sPQk = sPQk + p * q; sYk = sYk + c.kf(K_Y_prev)[i];
+        nL += c.Leff[F + i];
+    }
+    sQ = bfly(sQ); sPQ = bfly(sPQ); sP = bfly(sP); sY = bfly(sY); sK = bfly(sK);
+    sQk = bfly(sQk); sPQk = bfly(sPQk); sYk = bfly(sYk);
+    nL = bfly_i(nL);
+    if (c.lane == 0) {
         double *s = c.scal;
-        double sQ = r[0], sPQ = r[1], sQk = r[3], sPQk = r[4], sY = r[5], sYk = r[6];
         double price_prev = s[S_price];
-        double price = sQ > 0.0 ? sPQ / sQ : r[2] / (double)F;
+        double price = sQ > 0.0 ? sPQ / sQ : sP / (double)F;
         double price_k = sQk > 0.0 ? sPQk / sQk : s[S_price_k];
         double Yreal = sY * s[S_init_price] + sYk * s[S_init_price_k];
         double Ynom = sY * price + sYk * price_k;
@@ -825,10 +898,11 @@ __device__ void phase_tracking(Ctx &c)
         s[S_Y_real] = Yreal; s[S_Y_nominal_tot] = Ynom;
         s[S_gdp_deflator] = Yreal > 0.0 ? Ynom / Yreal : 0.0;
         s[S_inflationRate] = price / price_prev - 1.0;
-        s[S_Un] = 1.0 - (double)c.misc[M_LSUM] / (double)L.W;
+        s[S_Un] = 1.0 - (double)nL / (double)L.W;
         s[S_consumption] = sPQ;
-        s[S_totK] = r[7];
+        s[S_totK] = sK;
     }
+    __syncwarp();
 }
 
 // a20 firms_go_bankrupt! (cats.py:404) + a21 _get_terminated (cats.py:483-486)
@@ -837,113 +911,102 @@ __device__ void phase_bankrupt(Ctx &c)
     const Layout &L = c.a->L;
     const int W = L.W, F = L.F, N = L.N;
     const double thr = c.par[P_E_threshold_scale] * c.scal[S_price];
-    unsigned char *bad = c.bad;
-    for (int j = c.tid; j < F + N; j += c.nt) {
-        double A = j < F ? c.cf(C_A)[j] : c.kf(K_A)[j - F];
-        double liq = j < F ? c.cf(C_liquidity)[j] : c.kf(K_liquidity)[j - F];
-        bad[j] = ((A <= thr) || (liq < 0.0)) ? 1 : 0;
+    unsigned char *bad = c.sm + L.s_bad;
+    // masked det_sums over the survivors / the defaulters, and survivor counts
+    double cK = 0.0, cL = 0.0, cP = 0.0, cY = 0.0, cLoss = 0.0, cDeb = 0.0;
+    double kL = 0.0, kP = 0.0, kY = 0.0, kLoss = 0.0, kDeb = 0.0;
+    int nsC = 0, nsK = 0;
+    for (int f = c.lane; f < F; f += 32) {
+        const double A = c.cf(C_A)[f], liq = c.cf(C_liquidity)[f], deb = c.cf(C_deb)[f];
+        const bool b = (A <= thr) || (liq < 0.0);
+        bad[f] = b ? 1 : 0;
+        nsC += b ? 0 : 1;
+        double expo = deb + (liq < 0.0 ? -liq : 0.0);
+        double loss = A < 0.0 ? -A : 0.0;
+        if (loss > expo) loss = expo;
+        cK = cK + (b ? 0.0 : c.cf(C_K)[f]);
+        cL = cL + (b ? 0.0 : liq);
+        cP = cP + (b ? 0.0 : c.cf(C_P)[f]);
+        cY = cY + (b ? 0.0 : c.cf(C_Y_prev)[f]);
+        cLoss = cLoss + (b ? loss : 0.0);
+        cDeb = cDeb + (b ? deb : 0.0);
     }
-    __syncthreads();
-    // 11 masked det_sums + 2 survivor counts
-    for (int q = c.warp; q < 13; q += c.nwarps) {
-        if (q >= 11) {
-            const int isk = q - 11;
-            int n = warp_int_sum(isk ? N : F, c.lane, [&](int i) { return bad[isk ? F + i : i] ? 0 : 1; });
-            if (c.lane == 0) c.misc[isk ? M_NS_K : M_NS_C] = n;
-            continue;
-        }
-        double s;
-        if (q < 6) {
-            const double *A = c.cf(C_A), *liq = c.cf(C_liquidity), *deb = c.cf(C_deb);
-            const double *x = q == 0 ? c.cf(C_K) : q == 1 ? liq : q == 2 ? c.cf(C_P) : c.cf(C_Y_prev);
-            s = warp_det_sum(F, c.lane, [&](int i) {
-                const bool b = bad[i] != 0;
-                if (q < 4) return b ? 0.0 : x[i];
-                if (q == 5) return b ? deb[i] : 0.0;
-                double lq = liq[i], a = A[i];
-                double expo = deb[i] + (lq < 0.0 ? -lq : 0.0);
-                double loss = a < 0.0 ? -a : 0.0;
-                if (loss > expo) loss = expo;
-                return b ? loss : 0.0;
-            });
-        } else {
-            const int qq = q - 6;  // 0 liq, 1 P, 2 Y_prev, 3 loss, 4 deb
-            const double *A = c.kf(K_A), *liq = c.kf(K_liquidity), *deb = c.kf(K_deb);
-            const double *x = qq == 0 ? liq : qq == 1 ? c.kf(K_P) : c.kf(K_Y_prev);
-            s = warp_det_sum(N, c.lane, [&](int i) {
-                const bool b = bad[F + i] != 0;
-                if (qq < 3) return b ? 0.0 : x[i];
-                if (qq == 4) return b ? deb[i] : 0.0;
-                double lq = liq[i], a = A[i];
-                double expo = deb[i] + (lq < 0.0 ? -lq : 0.0);
-                double loss = a < 0.0 ? -a : 0.0;
-                if (loss > expo) loss = expo;
-                return b ? loss : 0.0;
-            });
-        }
-        if (c.lane == 0) c.red[R_SUM + q] = s;
+    for (int i = c.lane; i < N; i += 32) {
+        const double A = c.kf(K_A)[i], liq = c.kf(K_liquidity)[i], deb = c.kf(K_deb)[i];
+        const bool b = (A <= thr) || (liq < 0.0);
+        bad[F + i] = b ? 1 : 0;
+        nsK += b ? 0 : 1;
+        double expo = deb + (liq < 0.0 ? -liq : 0.0);
+        double loss = A < 0.0 ? -A : 0.0;
+        if (loss > expo) loss = expo;
+        kL = kL + (b ? 0.0 : liq);
+        kP = kP + (b ? 0.0 : c.kf(K_P)[i]);
+        kY = kY + (b ? 0.0 : c.kf(K_Y_prev)[i]);
+        kLoss = kLoss + (b ? loss : 0.0);
+        kDeb = kDeb + (b ? deb : 0.0);
     }
-    __syncthreads();
-    if (c.tid == 0) {
-        const double *r = c.red + R_SUM;
-        double *mean = c.red + R_MEAN;
-        int nsC = c.misc[M_NS_C], nsK = c.misc[M_NS_K];
-        double mK = 10.0, mL = 0.0, mP = c.scal[S_price], mY = c.par[P_alpha];
-        if (nsC > 0) { mK = r[0] / (double)nsC; mL = r[1] / (double)nsC; mP = r[2] / (double)nsC; mY = r[3] / (double)nsC; }
-        mean[0] = mK; mean[1] = mL; mean[2] = mP; mean[3] = mY;
-        double bd = c.scal[S_bank_bad_debt] + r[4];
-        double loans = c.scal[S_bank_loans] - r[5];
-        double mLk = 0.0, mPk = c.scal[S_price_k], mYk = c.par[P_alpha];
-        if (nsK > 0) { mLk = r[6] / (double)nsK; mPk = r[7] / (double)nsK; mYk = r[8] / (double)nsK; }
-        mean[4] = mLk; mean[5] = mPk; mean[6] = mYk;
-        bd = bd + r[9];
-        loans = loans - r[10];
+    cK = bfly(cK); cL = bfly(cL); cP = bfly(cP); cY = bfly(cY); cLoss = bfly(cLoss); cDeb = bfly(cDeb);
+    kL = bfly(kL); kP = bfly(kP); kY = bfly(kY); kLoss = bfly(kLoss); kDeb = bfly(kDeb);
+    nsC = bfly_i(nsC); nsK = bfly_i(nsK);
+    double mK = 10.0, mL = 0.0, mP = c.scal[S_price], mY = c.par[P_alpha];
+    if (nsC > 0) { mK = cK / (double)nsC; mL = cL / (double)nsC; mP = cP / (double)nsC; mY = cY / (double)nsC; }
+    double mLk = 0.0, mPk = c.scal[S_price_k], mYk = c.par[P_alpha];
+    if (nsK > 0) { mLk = kL / (double)nsK; mPk = kP / (double)nsK; mYk = kY / (double)nsK; }
+    const double price_k = c.scal[S_price_k];
+    __syncwarp();
+    if (c.lane == 0) {
+        double bd = c.scal[S_bank_bad_debt] + cLoss;
+        double loans = c.scal[S_bank_loans] - cDeb;
+        bd = bd + kLoss;
+        loans = loans - kDeb;
         c.scal[S_bank_bad_debt] = bd; c.scal[S_bank_loans] = loans;
         c.scal[S_bankruptcy_rate] = (double)((F - nsC) + (N - nsK)) / (double)(F + N);
     }
-    __syncthreads();
-    const double *mean = c.red + R_MEAN;
-    for (int j = c.tid; j < F + N; j += c.nt) {
-        if (!bad[j]) continue;
-        if (j < F) {
-            const int f = j, ow = W + f;
-            double inj = mean[1] > 0.0 ? mean[1] : 0.0;
+    const int nbad = (F - nsC) + (N - nsK);
+    if (nbad > 0) {
+        for (int f = c.lane; f < F; f += 32) {
+            if (!bad[f]) continue;
+            const int ow = W + f;
+            double inj = mL > 0.0 ? mL : 0.0;
             double pa = c.PA[ow];
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
             c.PA[ow] = pa - inj;
-            double mK = mean[0], mY = mean[3];
-            double cv = mK * c.scal[S_price_k];
+            double cv = mK * price_k;
             c.cf(C_liquidity)[f] = inj; c.cf(C_K)[f] = mK; c.cf(C_capital_value)[f] = cv;
-            c.cf(C_A)[f] = inj + cv; c.cf(C_deb)[f] = 0.0; c.cf(C_P)[f] = mean[2];
+            c.cf(C_A)[f] = inj + cv; c.cf(C_deb)[f] = 0.0; c.cf(C_P)[f] = mP;
             c.cf(C_Y_prev)[f] = mY; c.cf(C_Yd)[f] = mY; c.cf(C_De)[f] = mY;
             c.cf(C_barYK)[f] = mY / c.par[P_k]; c.cf(C_interest_r)[f] = c.par[P_r_f];
             c.cf(C_Q)[f] = 0.0; c.cf(C_investment)[f] = 0.0; c.cf(C_wages)[f] = 0.0;
             c.cf(C_interests)[f] = 0.0; c.cf(C_div_income)[f] = 0.0;
             c.Leff[f] = 0;
-        } else {
-            const int i = j - F, ow = W + F + i;
-            double inj = mean[4] > 0.0 ? mean[4] : 0.0;
+        }
+        for (int i = c.lane; i < N; i += 32) {
+            if (!bad[F + i]) continue;
+            const int ow = W + F + i;
+            double inj = mLk > 0.0 ? mLk : 0.0;
             double pa = c.PA[ow];
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
             c.PA[ow] = pa - inj;
-            double mY = mean[6];
             c.kf(K_liquidity)[i] = inj; c.kf(K_A)[i] = inj; c.kf(K_deb)[i] = 0.0;
-            c.kf(K_P)[i] = mean[5]; c.kf(K_Y_prev)[i] = mY; c.kf(K_Yd)[i] = mY; c.kf(K_Yavail)[i] = mY;
-            c.kf(K_De)[i] = mY; c.kf(K_inv)[i] = 0.0; c.kf(K_interest_r)[i] = c.par[P_r_f];
+            c.kf(K_P)[i] = mPk; c.kf(K_Y_prev)[i] = mYk; c.kf(K_Yd)[i] = mYk; c.kf(K_Yavail)[i] = mYk;
+            c.kf(K_De)[i] = mYk; c.kf(K_inv)[i] = 0.0; c.kf(K_interest_r)[i] = c.par[P_r_f];
             c.kf(K_Q)[i] = 0.0; c.kf(K_wages)[i] = 0.0; c.kf(K_interests)[i] = 0.0;
             c.kf(K_div_income)[i] = 0.0;
             c.Leff[F + i] = 0;
         }
+        for (int w = c.lane; w < W; w += 32) { int o = c.Oc[w]; if (o >= 0 && bad[o]) c.Oc[w] = -1; }
     }
-    for (int w = c.tid; w < W; w += c.nt) { int o = c.Oc[w]; if (o >= 0 && bad[o]) c.Oc[w] = -1; }
-    __syncthreads();
-    if (c.warp == 0) {
+    __syncwarp();
+    {
         const double *A = c.cf(C_A);
-        double s = warp_det_sum(F, c.lane, [&](int i) { return A[i]; });
+        double s = 0.0;
+        for (int f = c.lane; f < F; f += 32) s = s + A[f];
+        s = bfly(s);
         if (c.lane == 0) c.scal[S_terminated] = s == 0.0 ? 1.0 : 0.0;
     }
+    __syncwarp();
 }
 
 // a22 bank_accounting!, a23 gov_accounting!, a24 adjust_wages!, a25 timestep (cats.py:407-413)
@@ -951,15 +1014,15 @@ __device__ void phase_closing(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int last = c.last;
-    if (c.tid == 0) {
+    double share = 0.0;
+    if (c.lane == 0) {
         double *s = c.scal;
         double gross = (s[S_bank_interest_income] + s[S_gov_r_b] * s[S_gov_bonds]) - s[S_bank_bad_debt];
         double dB = 0.0;
         if (gross > 0.0 && s[S_bank_E] > 0.0) dB = c.par[P_div] * gross;
         s[S_bank_E] = s[S_bank_E] + (gross - dB);
         s[S_dividendsB] = dB; s[S_profitsB] = gross;
-        c.red[R_SUM + 0] = dB > 0.0 ? dB / (double)(L.F + L.N) : 0.0;
-        c.misc[M_NBAD] = dB > 0.0 ? 1 : 0;
+        share = dB > 0.0 ? dB / (double)(L.F + L.N) : 0.0;
         if (last >= 27) {
             s[S_gov_G] = s[S_gov_G] + s[S_gov_r_b] * s[S_gov_bonds];
             double GB = s[S_gov_TA] - s[S_gov_G];
@@ -974,11 +1037,10 @@ __device__ void phase_closing(Ctx &c)
         }
         if (last >= 29) s[S_timestep] = s[S_timestep] + 1.0;
     }
-    __syncthreads();
-    if (c.misc[M_NBAD]) {
-        double share = c.red[R_SUM + 0];
-        for (int h = L.W + c.tid; h < L.H; h += c.nt) c.PA[h] = c.PA[h] + share;
-    }
+    share = __shfl_sync(FULL, share, 0);
+    if (share > 0.0)
+        for (int h = L.W + c.lane; h < L.H; h += 32) c.PA[h] = c.PA[h] + share;
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -989,181 +1051,178 @@ __device__ void run_period(Ctx &c)
     const KArgs &a = *c.a;
     const int F = a.L.F, N = a.L.N, last = c.last;
     long long t0 = 0;
-    if (a.cycles && c.tid == 0 && blockIdx.x == 0) t0 = clock64();
-#define TICK(slot) do { if (a.cycles && c.tid == 0 && blockIdx.x == 0) { long long t1 = clock64(); a.cycles[slot] += t1 - t0; t0 = t1; } } while (0)
+    const bool prof = a.cycles && c.lane == 0 && blockIdx.x == 0;
+    if (prof) t0 = clock64();
+#define TICK(slot) do { if (prof) { long long t1 = clock64(); a.cycles[slot] += t1 - t0; t0 = t1; } } while (0)
     // phases 1-2: reset_gov_and_banking_variables!, set_bond_interest_rate! (cats.py:355-356)
-    if (c.tid == 0) {
+    if (c.lane == 0) {
         c.scal[S_gov_TA] = 0.0; c.scal[S_gov_G] = 0.0;
         c.scal[S_bank_interest_income] = 0.0; c.scal[S_bank_bad_debt] = 0.0;
         if (last >= 2) c.scal[S_gov_r_b] = c.par[P_interest_rate];
         c.misc[M_STATUS] = 0;
     }
-    __syncthreads();
+    __syncwarp();
     if (last < 3) return;
     phase_firm_decisions(c);  // 3..10
-    __syncthreads();
     TICK(0);
     if (last < 11) return;
     phase_fire(c, last >= 12 ? F + N : F);  // 11, 12
-    __syncthreads();
+    __syncwarp();
     TICK(1);
     if (last < 13) return;
     phase_job_search<ZM>(c);  // 13
-    __syncthreads();
+    __syncwarp();
     TICK(2);
     if (last < 14) return;
     phase_produce(c);         // 14, 15
-    __syncthreads();
     TICK(3);
     if (last < 16) return;
     phase_capital_market<ZM>(c);  // 16
-    __syncthreads();
     TICK(4);
     if (last < 17) return;
     phase_gov_income(c);      // 17 (+ government side of 18)
-    __syncthreads();
     TICK(5);
     if (last < 18) return;
-    if (last < 20) { phase_households_only(c); __syncthreads(); return; }
+    if (last < 20) { phase_households_only(c); return; }
     phase_goods_market<ZM>(c);  // 18, 19, 20
-    __syncthreads();
     TICK(6);
     if (last < 21) return;
     phase_accounting(c);      // 21, 22
-    __syncthreads();
     TICK(7);
     if (last < 23) return;
     phase_reward(c);          // 23
-    __syncthreads();
+    __syncwarp();
     TICK(8);
     if (last < 24) return;
     phase_tracking(c);        // 24
-    __syncthreads();
     TICK(9);
     if (last < 25) return;
     phase_bankrupt(c);        // 25
-    __syncthreads();
     TICK(10);
     if (last < 26) return;
     phase_closing(c);         // 26..29
-    __syncthreads();
     TICK(11);
 #undef TICK
 }
 
-template <int NT, int ZM, int MINB>
-__global__ void __launch_bounds__(NT, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
+template <int ZM, int MINB>
+__global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout &L = a.L;
     Ctx c;
     c.sm = smem; c.a = &a;
     c.scal = reinterpret_cast<double *>(smem + L.o_scal);
-    c.par = reinterpret_cast<double *>(smem + L.o_par);
+    c.par = reinterpret_cast<double *>(smem + L.s_par);
     c.Leff = reinterpret_cast<int *>(smem + L.o_Leff);
-    c.Ld = reinterpret_cast<int *>(smem + L.o_Ld);
-    c.vac = reinterpret_cast<int *>(smem + L.o_vac);
-    c.Oc = reinterpret_cast<int *>(smem + L.o_Oc);
-    c.red = reinterpret_cast<double *>(smem + L.o_red);
-    c.misc = reinterpret_cast<int *>(smem + L.o_misc);
-    c.bad = smem + L.o_bad;
-    c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-    c.nt = NT; c.nwarps = NT / 32;
+    c.Ld = reinterpret_cast<int *>(smem + L.s_Ld);
+    c.vac = reinterpret_cast<int *>(smem + L.s_vac);
+    c.misc = reinterpret_cast<int *>(smem + L.s_misc);
+    c.lane = threadIdx.x; c.lt = (1u << threadIdx.x) - 1u;
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.o_misc + 192);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 16);
+    const long long b = blockIdx.x;
+    if (b >= a.B) return;
+    c.b = b;
+    unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
+    c.blob = blob;
+    c.Oc = reinterpret_cast<int *>(blob + L.o_Oc);
+    c.PA = reinterpret_cast<double *>(blob + L.o_PA);
+    c.perm = reinterpret_cast<double *>(blob + L.o_perm);
 
-    c.goods_epoch = 0u;
-    if (c.tid == 0) {
+    // HBM -> smem: one TMA bulk copy of the resident prefix (aggregates, K-firm tables, head-counts)
+    if (c.lane == 0) {
         mbar_init(bar, 1);
-        uint64_t *ring = reinterpret_cast<uint64_t *>(smem + L.o_misc + 128);
-        for (int i = 0; i < 2 * GOODS_SLOTS; ++i) mbar_init(&ring[i], 1);
         fence_mbar_init();
+        mbar_expect_tx(bar, (uint32_t)L.resident);
+        bulk_g2s(smem, blob, (uint32_t)L.resident, bar);
     }
-    __syncthreads();
-    uint32_t parity = 0;
+    // parameters (shared row or per-economy row) while the copy is in flight
+    const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
+    for (int i = c.lane; i < N_PARAMS; i += 32) c.par[i] = pr[i];
+    if (c.lane == 0) c.par[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
+    // zero the transients (debug images are deterministic; the queue masks must start clear)
+    for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
+    __syncwarp();
+    mbar_wait(bar, 0);
+    __syncwarp();
 
-    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-        c.b = b;
-        unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
-        c.blob = blob;
-        c.PA = reinterpret_cast<double *>(blob + L.o_PA);
-        c.perm = reinterpret_cast<double *>(blob + L.o_perm);
-        // HBM -> smem: one TMA bulk copy of the resident prefix (firm tables, employment links)
-        if (c.tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)L.resident);
-            bulk_g2s(smem, blob, (uint32_t)L.resident, bar);
-        }
-        // parameters (shared row or per-economy row) while the copy is in flight
-        const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
-        for (int i = c.tid; i < N_PARAMS; i += NT) c.par[i] = pr[i];
-        if (c.tid == 0) c.par[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
-        // zero the transients so that debug images are deterministic
-        for (int i = L.resident / 4 + c.tid; i < L.workset / 4; i += NT) reinterpret_cast<int *>(smem)[i] = 0;
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        __syncthreads();
+    c.d.k0 = a.k0; c.d.k1 = a.k1;
+    c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
+    c.d.t = a.T;
+    c.d.z_c = (int)c.par[P_z_c]; c.d.z_k = (int)c.par[P_z_k]; c.d.z_e = (int)c.par[P_z_e];
 
-        c.d.k0 = a.k0; c.d.k1 = a.k1;
-        c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
-        c.d.t = a.T;
-        c.d.z_c = (int)c.par[P_z_c]; c.d.z_k = (int)c.par[P_z_k]; c.d.z_e = (int)c.par[P_z_e];
-
-        for (int t = 0; t < a.n_periods; ++t) {
-            c.d.period = (uint32_t)c.scal[S_timestep];
-            c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
-            run_period<ZM>(c);
-            __syncthreads();
-            if (a.stats && c.tid < N_STATS) {
-                const double *s = c.scal;
-                double v;
-                switch (c.tid) {
-                case 0: v = s[S_Y_real]; break;       case 1: v = s[S_wb]; break;
-                case 2: v = s[S_Un]; break;           case 3: v = s[S_bankruptcy_rate]; break;
-                case 4: v = s[S_price]; break;        case 5: v = s[S_Y_nominal_tot]; break;
-                case 6: v = s[S_gdp_deflator]; break; case 7: v = s[S_inflationRate]; break;
-                case 8: v = s[S_consumption]; break;  case 9: v = s[S_totK]; break;
-                case 10: v = s[S_dividendsB]; break;  case 11: v = s[S_profitsB]; break;
-                case 12: v = s[S_GB]; break;          case 13: v = s[S_deficitGDP]; break;
-                case 14: v = s[S_gov_bonds]; break;   default: v = s[S_price_k]; break;
-                }
-                a.stats[((size_t)b * (size_t)a.n_periods + (size_t)t) * N_STATS + c.tid] = v;
+    for (int t = 0; t < a.n_periods; ++t) {
+        c.d.period = (uint32_t)c.scal[S_timestep];
+        c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
+        run_period<ZM>(c);
+        __syncwarp();
+        if (a.stats && c.lane < N_STATS) {
+            const double *s = c.scal;
+            double v;
+            switch (c.lane) {
+            case 0: v = s[S_Y_real]; break;       case 1: v = s[S_wb]; break;
+            case 2: v = s[S_Un]; break;           case 3: v = s[S_bankruptcy_rate]; break;
+            case 4: v = s[S_price]; break;        case 5: v = s[S_Y_nominal_tot]; break;
+            case 6: v = s[S_gdp_deflator]; break; case 7: v = s[S_inflationRate]; break;
+            case 8: v = s[S_consumption]; break;  case 9: v = s[S_totK]; break;
+            case 10: v = s[S_dividendsB]; break;  case 11: v = s[S_profitsB]; break;
+            case 12: v = s[S_GB]; break;          case 13: v = s[S_deficitGDP]; break;
+            case 14: v = s[S_gov_bonds]; break;   default: v = s[S_price_k]; break;
             }
-            if (c.tid == 0 && c.misc[M_STATUS])
-                c.scal[S_status] = (double)((unsigned)c.scal[S_status] | (unsigned)c.misc[M_STATUS]);
+            a.stats[((size_t)b * (size_t)a.n_periods + (size_t)t) * N_STATS + c.lane] = v;
         }
-        __syncthreads();
-        // a26 _get_obs (cats.py:466-481 / 655-671), a21 terminated, status
-        if (a.obs) {
-            for (int i = c.tid; i < a.n_agents; i += NT) {
-                double yp = c.cf(C_Y_prev)[i], yd = c.cf(C_Yd)[i], p = c.cf(C_P)[i], ap = c.scal[S_price];
-                double o0, o1;
-                if (a.flags & CATS_FLAG_LOG) {
-                    o0 = det_log(yp + 1e-8) - det_log(yd + 1e-8);
-                    o1 = det_log(p + 1e-8) - det_log(ap + 1e-8);
-                } else { o0 = yp - yd; o1 = p - ap; }
-                a.obs[2 * (b * a.n_agents + i)] = o0;
-                a.obs[2 * (b * a.n_agents + i) + 1] = o1;
-            }
+        if (c.lane == 0 && c.misc[M_STATUS])
+            c.scal[S_status] = (double)((unsigned)c.scal[S_status] | (unsigned)c.misc[M_STATUS]);
+        __syncwarp();
+    }
+    // a26 _get_obs (cats.py:466-481 / 655-671), a21 terminated, status
+    if (a.obs) {
+        for (int i = c.lane; i < a.n_agents; i += 32) {
+            double yp = c.cf(C_Y_prev)[i], yd = c.cf(C_Yd)[i], p = c.cf(C_P)[i], ap = c.scal[S_price];
+            double o0, o1;
+            if (a.flags & CATS_FLAG_LOG) {
+                o0 = det_log(yp + 1e-8) - det_log(yd + 1e-8);
+                o1 = det_log(p + 1e-8) - det_log(ap + 1e-8);
+            } else { o0 = yp - yd; o1 = p - ap; }
+            a.obs[2 * (b * a.n_agents + i)] = o0;
+            a.obs[2 * (b * a.n_agents + i) + 1] = o1;
         }
-        if (c.tid == 0) {
-            if (a.terminated) a.terminated[b] = c.scal[S_terminated] != 0.0 ? 1 : 0;
-            if (a.status) a.status[b] = (unsigned)c.scal[S_status];
+    }
+    if (c.lane == 0) {
+        if (a.terminated) a.terminated[b] = c.scal[S_terminated] != 0.0 ? 1 : 0;
+        if (a.status) a.status[b] = (unsigned)c.scal[S_status];
+    }
+    if (a.debug) {
+        // transients image (cats_workset_field_info): Ld vac cFtot cKdem cYstock cvalinv kFtot kYstock
+        unsigned char *img = a.debug + (size_t)b * (size_t)L.workset;
+        const int nf = L.F + L.N;
+        const MktRec *mkt = reinterpret_cast<const MktRec *>(smem + L.s_U);
+        const bool have_mkt = c.last >= 14;
+        for (int i = c.lane; i < L.workset / 4; i += 32) reinterpret_cast<int *>(img)[i] = 0;
+        __syncwarp();
+        for (int i = c.lane; i < nf; i += 32) {
+            reinterpret_cast<int *>(img + L.d_Ld)[i] = c.Ld[i];
+            reinterpret_cast<int *>(img + L.d_vac)[i] = c.vac[i];
         }
-        if (a.debug) {
-            const int4 *src = reinterpret_cast<const int4 *>(smem);
-            int4 *dst = reinterpret_cast<int4 *>(a.debug + (size_t)b * (size_t)L.workset);
-            for (int i = c.tid; i < L.workset / 16; i += NT) dst[i] = src[i];
+        for (int f = c.lane; f < L.F; f += 32) {
+            reinterpret_cast<double *>(img + L.d_cFtot)[f] = c.at(L.s_cFtot)[f];
+            reinterpret_cast<double *>(img + L.d_cKdem)[f] = c.at(L.s_cKdem)[f];
+            reinterpret_cast<double *>(img + L.d_cYstock)[f] = have_mkt ? mkt[f].ys : 0.0;
+            reinterpret_cast<double *>(img + L.d_cvalinv)[f] = c.at(L.s_cvalinv)[f];
         }
-        // smem -> HBM: bulk store of the resident prefix
-        fence_proxy_async();
-        __syncthreads();
-        if (c.tid == 0) {
-            bulk_s2g(blob, smem, (uint32_t)L.resident);
-            bulk_commit();
-            bulk_wait_all();
+        for (int i = c.lane; i < L.N; i += 32) {
+            reinterpret_cast<double *>(img + L.d_kFtot)[i] = c.at(L.s_kFtot)[i];
+            reinterpret_cast<double *>(img + L.d_kYstock)[i] = c.at(L.s_kYstock)[i];
         }
-        __syncthreads();
+    }
+    // smem -> HBM: bulk store of the resident prefix
+    fence_proxy_async();
+    __syncwarp();
+    if (c.lane == 0) {
+        bulk_s2g(blob, smem, (uint32_t)L.resident);
+        bulk_commit();
+        bulk_wait_all();
     }
 }
 
@@ -1212,13 +1271,16 @@ using namespace cats;
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
-constexpr int kThreads = 64;    // threads per economy block: one market consumer warp + one producer warp
-constexpr int kMinBlocks = 8;   // __launch_bounds__ hint: register budget for >= 8 resident economies / SM
+constexpr int kThreads = 32;    // one warp per economy
+#ifndef CATS_MIN_BLOCKS
+#define CATS_MIN_BLOCKS 16
+#endif
+constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
 typedef void (*KernelFn)(const KArgs);
 static KernelFn select_kernel(int max_z)
 {
-    if (max_z > 0 && max_z <= 5) return cats_period_kernel<kThreads, 5, kMinBlocks>;
-    return cats_period_kernel<kThreads, MAX_Z, kMinBlocks>;
+    if (max_z > 0 && max_z <= 5) return cats_period_kernel<5, kMinBlocks>;
+    return cats_period_kernel<MAX_Z, kMinBlocks>;
 }
 
 static int fail(int code, const char *fmt, const char *detail)
@@ -1300,11 +1362,11 @@ int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byt
     if (!name || !byte_offset || !count || !dtype) return fail(CATS_EINVAL, "null argument%s", "");
     Layout L = make_layout(W, F, N);
     struct T { const char *n; uint64_t off; int cnt; int dt; } t[] = {
-        {"c_Ld", (uint64_t)L.o_Ld, F, 1}, {"k_Ld", (uint64_t)L.o_Ld + 4ull * F, N, 1},
-        {"c_vac", (uint64_t)L.o_vac, F, 1}, {"k_vac", (uint64_t)L.o_vac + 4ull * F, N, 1},
-        {"c_Ftot", (uint64_t)L.o_cFtot, F, 0}, {"c_Kdem", (uint64_t)L.o_cKdem, F, 0},
-        {"c_Ystock", (uint64_t)L.o_cYstock, F, 0}, {"c_valinv", (uint64_t)L.o_cvalinv, F, 0},
-        {"k_Ftot", (uint64_t)L.o_kFtot, N, 0}, {"k_Ystock", (uint64_t)L.o_kYstock, N, 0},
+        {"c_Ld", (uint64_t)L.d_Ld, F, 1}, {"k_Ld", (uint64_t)L.d_Ld + 4ull * F, N, 1},
+        {"c_vac", (uint64_t)L.d_vac, F, 1}, {"k_vac", (uint64_t)L.d_vac + 4ull * F, N, 1},
+        {"c_Ftot", (uint64_t)L.d_cFtot, F, 0}, {"c_Kdem", (uint64_t)L.d_cKdem, F, 0},
+        {"c_Ystock", (uint64_t)L.d_cYstock, F, 0}, {"c_valinv", (uint64_t)L.d_cvalinv, F, 0},
+        {"k_Ftot", (uint64_t)L.d_kFtot, N, 0}, {"k_Ystock", (uint64_t)L.d_kYstock, N, 0},
     };
     for (auto &e : t)
         if (!strcmp(name, e.n)) { *byte_offset = e.off; *count = e.cnt; *dtype = e.dt; return CATS_OK; }
@@ -1411,9 +1473,9 @@ int cats_step(const cats_step_args *s)
     int occ = 0, sms = 0;
     KernelFn fn = select_kernel(s->max_z);
     if (int rc = configure_kernel(a.L, fn, &occ, &sms)) return rc;
-    long long grid = (long long)occ * sms;
-    if (grid > s->B) grid = s->B;
-    fn<<<(unsigned)grid, kThreads, a.L.smem, (cudaStream_t)s->stream>>>(a);
+    // one block (= one warp) per economy: the hardware block scheduler balances economies of
+    // different length over the SMs; `occ` of them are resident per SM
+    fn<<<(unsigned)s->B, kThreads, a.L.smem, (cudaStream_t)s->stream>>>(a);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));

@@ -1,18 +1,18 @@
 // cats_layout.h -- economy blob / on-chip working-set layout shared by host and device code.
 //
-// One economy = one contiguous blob in HBM (docs/MODEL.md section 2, docs/DESIGN.md "data layout"):
+// One economy = one contiguous blob in HBM (docs/MODEL.md section 2, DESIGN.md "data layout"):
 //
-//   [ scal | K-firm rows | Leff | Oc |  C-firm rows | PA | perm ]
-//     `------ resident prefix -------'  `------ streamed tail -----'
+//   [ scal | K-firm rows | Leff |  Oc | C-firm rows | PA | perm ]
+//     `---- resident prefix ----'  `------- streamed tail -------'
 //
-// The resident prefix (aggregates, K-firm tables, head-counts, employment links: what the labour
-// and capital-goods markets touch at random) is pulled into shared memory with one TMA bulk copy
-// and pushed back with one bulk store.  The tail is streamed from global memory / L2: C-firm rows
-// are only ever touched by "their" thread (coalesced), and the consumption-goods market works on
-// a packed per-seller record table built in shared memory when it opens; household wealth and
-// permanent income are read and written once per period inside the goods loop.  Keeping the tail
-// out of shared memory is what lets ~8 economies be resident per SM instead of 3, and the step is
-// latency-bound, so residency is throughput.
+// One WARP advances one economy.  The resident prefix (aggregates, K-firm tables, head-counts: what
+// the labour and capital-goods markets touch at random) is pulled into shared memory with one TMA
+// bulk copy and pushed back with one bulk store.  The tail is streamed through L2: C-firm rows are
+// only ever touched by the lane that owns the firm (lane l owns firms l, l+32, ...: coalesced, and
+// it makes the fixed-order fp64 reductions register-only), employment links and household wealth /
+// permanent income are gathered once per market in visiting order.  The consumption-goods market
+// works on a packed per-seller record table in shared memory.  Keeping the tail out of shared
+// memory leaves ~10 KB per economy on chip, so residency is bounded by registers, not smem.
 // All section offsets are multiples of 16 bytes (bulk-copy granularity).
 #pragma once
 #include <stdint.h>
@@ -55,11 +55,17 @@ struct Layout {
     int32_t W, F, N, H;
     int32_t rowF, rowN;  // bytes of one firm f64 row
     // persisted sections (byte offsets inside the blob)
-    int32_t o_scal, o_k, o_Leff, o_Oc, resident, o_c, o_PA, o_perm, blob;
-    // transients (byte offsets inside the shared-memory working set; all >= resident)
-    int32_t o_Ld, o_vac, o_cFtot, o_cKdem, o_cYstock, o_cvalinv, o_kFtot, o_kYstock, workset;
-    // scratch that is never dumped
-    int32_t o_scr, scr_bytes, o_ring, o_bad, o_red, o_par, o_misc, smem;
+    int32_t o_scal, o_k, o_Leff, resident, o_Oc, o_c, o_PA, o_perm, blob;
+    // shared-memory working set: [0, resident) mirrors the blob prefix, then
+    int32_t s_Ld, s_vac;            // int32 x (F+N): labour demand, vacancies (negative = surplus)
+    int32_t s_cFtot, s_cKdem, s_cvalinv, s_kFtot, s_kYstock;  // f64 transients
+    int32_t s_icnt, s_icur;         // int32 x (F+N): firing buckets / capital-market buyer list
+    int32_t s_pmask;                // uint32 x F: lanes queueing at a sold-out seller (goods market)
+    int32_t s_bad;                  // uint8 x (F+N): bankrupt flags
+    int32_t s_U, U_bytes;           // union: goods-market seller records | firing pool | job seekers
+    int32_t s_par, s_misc, smem;
+    // debug image (cats_workset_*): transients dumped after a stop_phase step
+    int32_t d_Ld, d_vac, d_cFtot, d_cKdem, d_cYstock, d_cvalinv, d_kFtot, d_kYstock, workset;
 };
 
 __host__ __device__ inline int32_t up16(int64_t x) { return (int32_t)((x + 15) & ~(int64_t)15); }
@@ -73,35 +79,46 @@ inline Layout make_layout(int W, int F, int N)
     L.o_scal = (int32_t)o; o += 8 * N_SCAL;
     L.o_k = (int32_t)o; o += (int64_t)NK_FIELDS * L.rowN;
     L.o_Leff = (int32_t)o; o += up16(4ll * (F + N));
+    L.resident = (int32_t)o;
     L.o_Oc = (int32_t)o; o += up16(4ll * W);
     o = (o + 127) & ~(int64_t)127;
-    L.resident = (int32_t)o;
     L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
     L.o_PA = (int32_t)o; o += up16(8ll * L.H);
     L.o_perm = (int32_t)o; o += up16(8ll * L.H);
     o = (o + 127) & ~(int64_t)127;
     L.blob = (int32_t)o;
-    // shared-memory image: [0, resident) mirrors the blob prefix, transients follow
+    // shared memory
     o = L.resident;
-    L.o_Ld = (int32_t)o; o += up16(4ll * (F + N));
-    L.o_vac = (int32_t)o; o += up16(4ll * (F + N));
-    L.o_cFtot = (int32_t)o; o += L.rowF;
-    L.o_cKdem = (int32_t)o; o += L.rowF;
-    L.o_cYstock = (int32_t)o; o += L.rowF;
-    L.o_cvalinv = (int32_t)o; o += L.rowF;
-    L.o_kFtot = (int32_t)o; o += L.rowN;
-    L.o_kYstock = (int32_t)o; o += L.rowN;
-    L.workset = (int32_t)o;
-    // scratch: fire pool (W x {worker, key}) / job seekers (W ints) / goods-market records
-    // ((F + 1) x 32 B, the last one a dummy) -- used at different times
-    L.o_scr = (int32_t)o; L.scr_bytes = up16(8ll * W > 32ll * (F + 1) ? 8ll * W : 32ll * (F + 1)); o += L.scr_bytes;
-    // goods-market producer/consumer ring: 2 slots of 32 prepared buyers (see GoodsSlot)
-    L.o_ring = (int32_t)o; o += 2 * (32 * (8 + 8 + 8 * MAX_Z + 4 * MAX_Z + 4));
-    L.o_bad = (int32_t)o; o += up16(F + N);
-    L.o_red = (int32_t)o; o += 8 * 64;
-    L.o_par = (int32_t)o; o += 8 * P_SLOTS;
-    L.o_misc = (int32_t)o; o += 256;
+    L.s_Ld = (int32_t)o; o += up16(4ll * (F + N));
+    L.s_vac = (int32_t)o; o += up16(4ll * (F + N));
+    L.s_cFtot = (int32_t)o; o += L.rowF;
+    L.s_cKdem = (int32_t)o; o += L.rowF;
+    L.s_cvalinv = (int32_t)o; o += L.rowF;
+    L.s_kFtot = (int32_t)o; o += L.rowN;
+    L.s_kYstock = (int32_t)o; o += L.rowN;
+    L.s_icnt = (int32_t)o; o += up16(4ll * (F + N));
+    L.s_icur = (int32_t)o; o += up16(4ll * (F + N));
+    L.s_pmask = (int32_t)o; o += up16(4ll * F);
+    L.s_bad = (int32_t)o; o += up16(F + N);
+    // union region: (F + 1) seller records of 32 B (the last one a dummy) | firing pool of
+    // {worker, key} pairs | job seekers (one int32 per worker)
+    int64_t u = 32ll * (F + 1);
+    if (4ll * W > u) u = 4ll * W;
+    L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
+    L.s_par = (int32_t)o; o += 8 * P_SLOTS;
+    L.s_misc = (int32_t)o; o += 64;
     L.smem = (int32_t)o;
+    // debug image
+    o = 0;
+    L.d_Ld = (int32_t)o; o += up16(4ll * (F + N));
+    L.d_vac = (int32_t)o; o += up16(4ll * (F + N));
+    L.d_cFtot = (int32_t)o; o += L.rowF;
+    L.d_cKdem = (int32_t)o; o += L.rowF;
+    L.d_cYstock = (int32_t)o; o += L.rowF;
+    L.d_cvalinv = (int32_t)o; o += L.rowF;
+    L.d_kFtot = (int32_t)o; o += L.rowN;
+    L.d_kYstock = (int32_t)o; o += L.rowN;
+    L.workset = (int32_t)o;
     return L;
 }
 

@@ -52,7 +52,7 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(args, world):
+def workload_config(args, world, blob_bytes=37760):
     return {
         "workload": f"{args.economies} default-size economies per GPU (W={W},F={F},N={N}, default ABCredit "
                     f"parameters), Monte-Carlo seeds, heuristic firms (n_agents=1, dummy action mask), "
@@ -60,7 +60,7 @@ def workload_config(args, world):
         "economies_per_gpu": args.economies, "economies_total": args.economies * world,
         "periods_per_step": 1, "W": W, "F": F, "N": N,
         "parallelism": f"economy-sharded x{world}, no step-path collective",
-        "l2_policy": "state per GPU (%.0f MB) exceeds L2 (126 MB); no flush" % (args.economies * 41088 / 1e6),
+        "l2_policy": "state per GPU (%.0f MB) exceeds L2 (126 MB); no flush" % (args.economies * blob_bytes / 1e6),
     }
 
 
@@ -249,7 +249,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": workload_config(args, world, env.blob_bytes),
             "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": env.h2d_bytes_per_step() + B, "d2h_bytes_per_step": env.d2h_bytes_per_step(True)},
             "gpu_launches": launches,

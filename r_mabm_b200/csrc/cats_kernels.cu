@@ -63,7 +63,7 @@ struct Ctx {
     unsigned char *blob;  // this economy's blob in global memory (Oc, C-firm rows, PA, perm live there)
     const KArgs *a;
     double *scal, *par;   // shared
-    int *Leff, *Ld, *vac; // shared
+    int *Leff, *vac;      // shared (labour demand Ld == Leff + vac)
     int *Oc;              // GLOBAL
     double *PA, *perm;    // GLOBAL
     double *mean;         // shared scratch: 8 doubles
@@ -74,7 +74,12 @@ struct Ctx {
     int last;             // last phase id to execute (stop_phase or 99)
     Draws d;
     __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + a->L.o_c + field * a->L.rowF); }  // GLOBAL
-    __device__ __forceinline__ double *kf(int field) const { return reinterpret_cast<double *>(sm + a->L.o_k + field * a->L.rowN); }
+    // K-firm rows: hot ones (P, Yd, Q) are SHARED, the others GLOBAL; `field` is a compile-time constant
+    __device__ __forceinline__ double *kf(int field) const
+    {
+        return field < NK_HOT ? reinterpret_cast<double *>(sm + a->L.o_kh + field * a->L.rowN)
+                              : reinterpret_cast<double *>(blob + a->L.o_kc + (field - NK_HOT) * a->L.rowN);
+    }
     __device__ __forceinline__ double *at(int off) const { return reinterpret_cast<double *>(sm + off); }
     __device__ __forceinline__ int *iat(int off) const { return reinterpret_cast<int *>(sm + off); }
 };
@@ -194,7 +199,7 @@ __device__ void phase_firm_decisions(Ctx &c)
             double aa = ceil(de / alpha);
             double bb = ceil((c.cf(C_K)[f] * c.par[P_k]) / alpha);
             int Ld = d2count(aa < bb ? aa : bb);
-            int vac = 0;
+            int vac = Ld - c.Leff[f];
             // phase 9: a8 firms_get_credit! (cats.py:376)
             if (last >= 9) {
                 double liq = c.cf(C_liquidity)[f];
@@ -205,7 +210,7 @@ __device__ void phase_firm_decisions(Ctx &c)
                 c.cf(C_deb)[f] = deb; c.cf(C_interest_r)[f] = ir; c.at(L.s_cFtot)[f] = Ftot;
                 accC = accC + Ftot;
             }
-            c.Ld[f] = Ld; c.vac[f] = vac;
+            c.vac[f] = vac;
         }
     }
     for (int i = c.lane; i < N; i += 32) {
@@ -229,7 +234,7 @@ __device__ void phase_firm_decisions(Ctx &c)
         // phase 8: a7 firms_decide_labour! for K-firms (cats.py:374)
         if (last >= 8) {
             int Ld = d2count(ceil(de / alpha));
-            int vac = 0;
+            int vac = Ld - c.Leff[F + i];
             // phase 10: a8 firms_get_credit! for K-firms (cats.py:377)
             if (last >= 10) {
                 double liq = c.kf(K_liquidity)[i];
@@ -240,7 +245,7 @@ __device__ void phase_firm_decisions(Ctx &c)
                 c.kf(K_deb)[i] = deb; c.kf(K_interest_r)[i] = ir; c.at(L.s_kFtot)[i] = Ftot;
                 accK = accK + Ftot;
             }
-            c.Ld[F + i] = Ld; c.vac[F + i] = vac;
+            c.vac[F + i] = vac;
         }
     }
     // bank loan stock: += det_sum(new credit), C-firms then K-firms
@@ -263,14 +268,14 @@ __device__ void phase_fire(Ctx &c, int limit)
 {
     const Layout &L = c.a->L;
     const int W = L.W, lane = c.lane;
-    int *icnt = c.iat(L.s_icnt), *icur = c.iat(L.s_icur);
+    int *ic = c.iat(L.s_ic);    // per firm: pooled head-count (low 16 bits) | pool cursor (high 16 bits)
     bool over = false;
-    for (int f = lane; f < limit; f += 32) { over |= c.vac[f] < 0; icnt[f] = 0; }
+    for (int f = lane; f < limit; f += 32) { over |= c.vac[f] < 0; ic[f] = 0; }
     if (!__any_sync(FULL, over)) return;
     __syncwarp();
     for (int w = lane; w < W; w += 32) {
         int f = c.Oc[w];
-        if (f >= 0 && f < limit && c.vac[f] < 0) atomicAdd(&icnt[f], 1);
+        if (f >= 0 && f < limit && c.vac[f] < 0) atomicAdd(&ic[f], 1);
     }
     __syncwarp();
     const int cap = L.U_bytes / 8;
@@ -283,13 +288,13 @@ __device__ void phase_fire(Ctx &c, int limit)
         bool stop = false;
         while (!stop && f1 < limit) {
             const int f = f1 + lane;
-            const int n = f < limit ? icnt[f] : 0;
+            const int n = f < limit ? ic[f] : 0;
             int incl = n;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
             const unsigned fm = __ballot_sync(FULL, base + incl <= cap);
             const int nfit = fm == FULL ? 32 : __ffs(~fm) - 1;
-            if (f < limit && lane < nfit) icur[f] = base + incl - n;
+            if (f < limit && lane < nfit) ic[f] = n | ((base + incl - n) << 16);
             const int add = __shfl_sync(FULL, incl, nfit > 0 ? nfit - 1 : 0);
             if (nfit > 0) base += add;
             f1 += nfit;
@@ -319,7 +324,7 @@ __device__ void phase_fire(Ctx &c, int limit)
                 if (lane == 0) c.Oc[bw] = -1;
                 __syncwarp();
             }
-            if (lane == 0) { c.Leff[f] = c.Ld[f]; c.vac[f] = 0; }
+            if (lane == 0) { c.Leff[f] = c.Leff[f] + c.vac[f]; c.vac[f] = 0; }
             __syncwarp();
             f0 = f + 1;
             continue;
@@ -329,7 +334,7 @@ __device__ void phase_fire(Ctx &c, int limit)
             for (int w = lane; w < W; w += 32) {
                 int f = c.Oc[w];
                 if (f >= f0 && f < f1 && c.vac[f] < 0) {
-                    int slot = atomicAdd(&icur[f], 1);
+                    int slot = atomicAdd(&ic[f], 0x10000) >> 16;
                     pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
                 }
             }
@@ -337,7 +342,8 @@ __device__ void phase_fire(Ctx &c, int limit)
             for (int i = lane; i < total; i += 32) {
                 const int w = pool_w[i]; const unsigned key = pool_k[i];
                 const int f = c.Oc[w];
-                const int end = icur[f], beg = end - icnt[f];
+                const int v = ic[f];
+                const int end = v >> 16, beg = end - (v & 0xffff);
                 int rank = 0;
                 for (int j = beg; j < end; ++j) {
                     const unsigned kj = pool_k[j]; const int wj = pool_w[j];
@@ -348,7 +354,7 @@ __device__ void phase_fire(Ctx &c, int limit)
             __syncwarp();
         }
         for (int f = f0 + lane; f < f1; f += 32)
-            if (c.vac[f] < 0) { c.Leff[f] = c.Ld[f]; c.vac[f] = 0; }
+            if (c.vac[f] < 0) { c.Leff[f] = c.Leff[f] + c.vac[f]; c.vac[f] = 0; }
         __syncwarp();
         f0 = f1;
     }
@@ -366,7 +372,7 @@ __device__ void phase_job_search(Ctx &c)
     const int W = L.W, nf = L.F + L.N, lane = c.lane;
     const int z = c.d.z_e < nf ? c.d.z_e : nf;
     Order ord; ord.init(c.d, MKT_JOB, W);
-    int *seekers = c.iat(L.s_U);
+    unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
     int total = 0;
     for (int base = 0; base < W; base += 128) {
         int w[4]; int oc[4];
@@ -381,7 +387,7 @@ __device__ void phase_job_search(Ctx &c)
         for (int q = 0; q < 4; ++q) {
             const bool un = oc[q] < 0;
             const unsigned bal = __ballot_sync(FULL, un);
-            if (un) seekers[total + __popc(bal & c.lt)] = w[q];
+            if (un) seekers[total + __popc(bal & c.lt)] = (unsigned short)w[q];
             total += __popc(bal);
         }
     }
@@ -391,7 +397,7 @@ __device__ void phase_job_search(Ctx &c)
         const int idx = base + lane;
         int w = -1;
         int cand[ZM];
-        if (idx < total) { w = seekers[idx]; c.d.candidates<ZM>(PH_JOB, w, nf, z, cand); }
+        if (idx < total) { w = (int)seekers[idx]; c.d.candidates<ZM>(PH_JOB, w, nf, z, cand); }
         unsigned pending = __ballot_sync(FULL, idx < total);
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
@@ -450,7 +456,6 @@ __device__ void phase_produce(Ctx &c)
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
         if (last < 20) { c.cf(C_Q)[f] = 0.0; c.cf(C_Yd)[f] = 0.0; }   // else written when the goods market closes
     }
-    if (c.lane == 0) { MktRec r; r.ys = 0.0; r.p = 1.0; r.q = 0.0; r.acc = 0ull; mkt[F] = r; }
     if (last >= 15) {
         for (int i = c.lane; i < N; i += 32) {
             double Leff = (double)c.Leff[F + i];
@@ -486,7 +491,7 @@ __device__ void phase_capital_market(Ctx &c)
     double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.s_kYstock);
     double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
     double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
-    int *buyers = c.iat(L.s_icnt);
+    int *buyers = c.iat(L.s_ic);
     int total = 0;
     for (int base = 0; base < F; base += 32) {
         const int pos = base + lane;
@@ -1115,7 +1120,6 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
     c.scal = reinterpret_cast<double *>(smem + L.o_scal);
     c.par = reinterpret_cast<double *>(smem + L.s_par);
     c.Leff = reinterpret_cast<int *>(smem + L.o_Leff);
-    c.Ld = reinterpret_cast<int *>(smem + L.s_Ld);
     c.vac = reinterpret_cast<int *>(smem + L.s_vac);
     c.misc = reinterpret_cast<int *>(smem + L.s_misc);
     c.lane = threadIdx.x; c.lt = (1u << threadIdx.x) - 1u;
@@ -1202,8 +1206,10 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         for (int i = c.lane; i < L.workset / 4; i += 32) reinterpret_cast<int *>(img)[i] = 0;
         __syncwarp();
         for (int i = c.lane; i < nf; i += 32) {
-            reinterpret_cast<int *>(img + L.d_Ld)[i] = c.Ld[i];
-            reinterpret_cast<int *>(img + L.d_vac)[i] = c.vac[i];
+            // Ld == Leff + vac; before the credit phase vac only carries Ld and reads as 0
+            const bool isk = i >= L.F;
+            reinterpret_cast<int *>(img + L.d_Ld)[i] = c.last >= (isk ? 8 : 7) ? c.Leff[i] + c.vac[i] : 0;
+            reinterpret_cast<int *>(img + L.d_vac)[i] = c.last >= (isk ? 10 : 9) ? c.vac[i] : 0;
         }
         for (int f = c.lane; f < L.F; f += 32) {
             reinterpret_cast<double *>(img + L.d_cFtot)[f] = c.at(L.s_cFtot)[f];
@@ -1245,7 +1251,7 @@ __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, co
         scal[S_gov_r_b] = par[P_interest_rate];
     }
     auto cf = [&](int f) { return reinterpret_cast<double *>(blob + L.o_c + f * L.rowF); };
-    auto kf = [&](int f) { return reinterpret_cast<double *>(blob + L.o_k + f * L.rowN); };
+    auto kf = [&](int f) { return reinterpret_cast<double *>(blob + (f < NK_HOT ? L.o_kh + f * L.rowN : L.o_kc + (f - NK_HOT) * L.rowN)); };
     for (int f = tid; f < L.F; f += nt) {
         cf(C_De)[f] = 1.0; cf(C_P)[f] = P0; cf(C_Y_prev)[f] = YC0; cf(C_Yd)[f] = YC0;
         cf(C_K)[f] = K0; cf(C_capital_value)[f] = K0 * PK0; cf(C_liquidity)[f] = LIQ0;
@@ -1292,7 +1298,7 @@ static int fail(int code, const char *fmt, const char *detail)
 static int check_sizes(int W, int F, int N)
 {
     if (W < 1 || F < 1 || N < 1) return fail(CATS_EINVAL, "W, F, N must be >= 1%s", "");
-    if ((long long)W + F + N > (1 << 24) || F + N > 65535) return fail(CATS_EINVAL, "economy too large%s", "");
+    if (W > 65535 || F + N > 32767) return fail(CATS_EINVAL, "economy too large for this build (W <= 65535, F + N <= 32767)%s", "");
     return CATS_OK;
 }
 
@@ -1343,7 +1349,9 @@ int cats_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset
         switch (d.kind) {
         case 0: *byte_offset = L.o_scal; *count = N_SCAL; *dtype = 0; break;
         case 1: *byte_offset = (uint64_t)L.o_c + (uint64_t)d.idx * L.rowF; *count = F; *dtype = 0; break;
-        case 2: *byte_offset = (uint64_t)L.o_k + (uint64_t)d.idx * L.rowN; *count = N; *dtype = 0; break;
+        case 2: *byte_offset = d.idx < NK_HOT ? (uint64_t)L.o_kh + (uint64_t)d.idx * L.rowN
+                                              : (uint64_t)L.o_kc + (uint64_t)(d.idx - NK_HOT) * L.rowN;
+                *count = N; *dtype = 0; break;
         case 3: *byte_offset = L.o_Leff; *count = F; *dtype = 1; break;
         case 4: *byte_offset = (uint64_t)L.o_Leff + 4ull * F; *count = N; *dtype = 1; break;
         case 5: *byte_offset = L.o_PA; *count = L.H; *dtype = 0; break;

@@ -2,8 +2,8 @@
 //
 // One economy = one contiguous blob in HBM (docs/MODEL.md section 2, DESIGN.md "data layout"):
 //
-//   [ scal | K-firm rows | Leff |  Oc | C-firm rows | PA | perm ]
-//     `---- resident prefix ----'  `------- streamed tail -------'
+//   [ scal | hot K-firm rows | Leff |  Oc | C-firm rows | cold K-firm rows | PA | perm ]
+//     `------ resident prefix -----'  `--------------- streamed tail ---------------'
 //
 // One WARP advances one economy.  The resident prefix (aggregates, K-firm tables, head-counts: what
 // the labour and capital-goods markets touch at random) is pulled into shared memory with one TMA
@@ -48,19 +48,21 @@ enum {
 // C-firm / K-firm float64 rows
 enum { C_De, C_P, C_Y_prev, C_Yd, C_Q, C_A, C_K, C_investment, C_capital_value, C_wages,
        C_interests, C_deb, C_liquidity, C_barYK, C_interest_r, C_div_income };
-enum { K_De, K_P, K_Y_prev, K_Yd, K_Q, K_A, K_wages, K_interests, K_deb, K_liquidity,
+// K-firm rows: the first NK_HOT are what the capital-goods market touches at random (resident in
+// shared memory); the others are only ever touched by the lane that owns the firm (streamed)
+enum { K_P, K_Yd, K_Q, K_De, K_Y_prev, K_A, K_wages, K_interests, K_deb, K_liquidity,
        K_interest_r, K_div_income, K_inv, K_Yavail };
+constexpr int NK_HOT = 3;
 
 struct Layout {
     int32_t W, F, N, H;
     int32_t rowF, rowN;  // bytes of one firm f64 row
     // persisted sections (byte offsets inside the blob)
-    int32_t o_scal, o_k, o_Leff, resident, o_Oc, o_c, o_PA, o_perm, blob;
+    int32_t o_scal, o_kh, o_Leff, resident, o_Oc, o_c, o_kc, o_PA, o_perm, blob;
     // shared-memory working set: [0, resident) mirrors the blob prefix, then
-    int32_t s_Ld, s_vac;            // int32 x (F+N): labour demand, vacancies (negative = surplus)
+    int32_t s_vac;                  // int32 x (F+N): vacancies (negative = surplus); Ld == Leff + vac
     int32_t s_cFtot, s_cKdem, s_cvalinv, s_kFtot, s_kYstock;  // f64 transients
-    int32_t s_icnt, s_icur;         // int32 x (F+N): firing buckets / capital-market buyer list
-    int32_t s_pmask;                // uint32 x F: lanes queueing at a sold-out seller (goods market)
+    int32_t s_ic;                   // int32 x (F+N): firing buckets (count | cursor << 16) / capital-market buyers
     int32_t s_bad;                  // uint8 x (F+N): bankrupt flags
     int32_t s_U, U_bytes;           // union: goods-market seller records | firing pool | job seekers
     int32_t s_par, s_misc, smem;
@@ -77,33 +79,31 @@ inline Layout make_layout(int W, int F, int N)
     L.rowF = up16(8ll * F); L.rowN = up16(8ll * N);
     int64_t o = 0;
     L.o_scal = (int32_t)o; o += 8 * N_SCAL;
-    L.o_k = (int32_t)o; o += (int64_t)NK_FIELDS * L.rowN;
+    L.o_kh = (int32_t)o; o += (int64_t)NK_HOT * L.rowN;
     L.o_Leff = (int32_t)o; o += up16(4ll * (F + N));
     L.resident = (int32_t)o;
     L.o_Oc = (int32_t)o; o += up16(4ll * W);
     o = (o + 127) & ~(int64_t)127;
     L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
+    L.o_kc = (int32_t)o; o += (int64_t)(NK_FIELDS - NK_HOT) * L.rowN;
     L.o_PA = (int32_t)o; o += up16(8ll * L.H);
     L.o_perm = (int32_t)o; o += up16(8ll * L.H);
     o = (o + 127) & ~(int64_t)127;
     L.blob = (int32_t)o;
     // shared memory
     o = L.resident;
-    L.s_Ld = (int32_t)o; o += up16(4ll * (F + N));
     L.s_vac = (int32_t)o; o += up16(4ll * (F + N));
     L.s_cFtot = (int32_t)o; o += L.rowF;
     L.s_cKdem = (int32_t)o; o += L.rowF;
     L.s_cvalinv = (int32_t)o; o += L.rowF;
     L.s_kFtot = (int32_t)o; o += L.rowN;
     L.s_kYstock = (int32_t)o; o += L.rowN;
-    L.s_icnt = (int32_t)o; o += up16(4ll * (F + N));
-    L.s_icur = (int32_t)o; o += up16(4ll * (F + N));
-    L.s_pmask = (int32_t)o; o += up16(4ll * F);
+    L.s_ic = (int32_t)o; o += up16(4ll * (F + N));
     L.s_bad = (int32_t)o; o += up16(F + N);
-    // union region: (F + 1) seller records of 32 B (the last one a dummy) | firing pool of
-    // {worker, key} pairs | job seekers (one int32 per worker)
-    int64_t u = 32ll * (F + 1);
-    if (4ll * W > u) u = 4ll * W;
+    // union region: F seller records of 32 B | firing pool of {worker, key} pairs | job seekers
+    // (one uint16 per worker: W <= 65535 in this build)
+    int64_t u = 32ll * F;
+    if (2ll * W > u) u = 2ll * W;
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;
     L.s_misc = (int32_t)o; o += 64;

@@ -1,4 +1,5 @@
-"""Quick device-side throughput probe (development aid, not the bench contract)."""
+"""Quick device-side throughput probe (development aid, not the bench contract).
+usage: quick_perf.py [B periods]..."""
 import sys, time
 sys.path.insert(0, ".")
 import torch
@@ -6,7 +7,7 @@ from r_mabm_b200.engine import BatchedCats
 
 def probe(B, periods, reps=3, **kw):
     env = BatchedCats(B, seed=1, **kw)
-    env.run(50)  # past the start-up transient
+    env.run(300)  # the reference burn-in: past the start-up transient
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
@@ -32,7 +33,13 @@ def phase_breakdown(B=148, periods=20):
 
 
 if __name__ == "__main__":
-    for B in (148, 1024, 4096):
-        probe(B, 20)
-    probe(1024, 1)
-    phase_breakdown()
+    a = [int(x) for x in sys.argv[1:]]
+    if a:
+        for i in range(0, len(a), 2):
+            probe(a[i], a[i + 1])
+    else:
+        for B in (148, 1024, 4096):
+            probe(B, 20)
+        probe(1024, 1)
+        probe(16384, 1)
+        phase_breakdown()

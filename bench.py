@@ -43,8 +43,8 @@ UNIT = "economy-periods/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--economies", type=int, default=ECONOMIES_PER_GPU, help="economies per GPU")
     ap.add_argument("--burnin", type=int, default=BURNIN)

@@ -774,14 +774,17 @@ void ph_cons_budget(Econ *e)
     }
 }
 
-/* Demand expressed at a consumption-goods seller is accumulated in 2^-40 fixed point (wrap-around
- * uint64 add), so that the sum does not depend on the order of the visits: docs/MODEL.md 4.4.
- * Every other quantity of the market (stock, sales, budgets) follows the visiting order exactly. */
+/* Demand expressed at a consumption-goods seller (docs/MODEL.md 4.4).  A visit by a household with
+ * budget b registers the demand b / P_seller.  The sum over the visits is order-independent by
+ * construction: each visit adds round(b * (1 / Pavg) * 2^40) to a wrap-around uint64 accumulator
+ * (Pavg = last period's average price: budgets in real units), and when the market closes
+ * Yd = acc * 2^-40 * Pavg / P_seller.  Every other quantity of the market (stock, sales, budgets)
+ * follows the visiting order exactly. */
 #define FX_ONE 1099511627776.0 /* 2^40 */
-static uint64_t fx_from(double d)
+static uint64_t fx_from(double x)
 {
-    if (!(d < 4194304.0)) return (uint64_t)1 << 62; /* saturate (also NaN, +inf: zero prices) */
-    return (uint64_t)(int64_t)llrint(d * FX_ONE); /* round to nearest even */
+    if (!(x < 4194304.0)) return (uint64_t)1 << 62; /* saturate (also NaN, +inf) */
+    return (uint64_t)(int64_t)llrint(x * FX_ONE);   /* round to nearest even */
 }
 static double fx_to(uint64_t a) { return (double)(int64_t)a * (1.0 / FX_ONE); }
 
@@ -791,6 +794,7 @@ void ph_goods_market(Econ *e)
     Order o; order_init(e, MKT_GOODS, e->H, &o);
     int z = e->z_c < e->F ? e->z_c : e->F;
     const double *P = e->c[C_P];
+    const double pavg = e->scal[S_price], rpavg = 1.0 / pavg;
     uint64_t *acc = (uint64_t *)xcalloc((size_t)e->F, 8);
     for (int pos = 0; pos < e->H; ++pos) {
         int h = order_at(&o, pos);
@@ -803,10 +807,10 @@ void ph_goods_market(Econ *e)
             if (!(b > 0.0)) break;
             int best = cand[k];
             double p = P[best];
-            double d = b / p;
-            acc[best] += fx_from(d);
+            acc[best] += fx_from(b * rpavg);
             double ys = e->c_Ystock[best];
             if (ys > 0.0) {
+                double d = b / p;
                 if (ys > d) {
                     e->c_Ystock[best] = ys - d;
                     e->c[C_Q][best] = e->c[C_Q][best] + d;
@@ -821,7 +825,7 @@ void ph_goods_market(Econ *e)
         e->PA[h] = e->PA[h] + b; /* involuntary saving */
         e->budget[h] = b;
     }
-    for (int f = 0; f < e->F; ++f) e->c[C_Yd][f] = fx_to(acc[f]);
+    for (int f = 0; f < e->F; ++f) e->c[C_Yd][f] = (fx_to(acc[f]) * pavg) / P[f];
     free(acc);
 }
 

@@ -136,8 +136,8 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
 struct Draws {
     const unsigned char *tape;  // nullptr => Philox
     uint32_t k0, k1, period, economy;
-    TapeOff t;
-    int z_c, z_k, z_e;
+    const TapeOff *tp;          // tape record layout (kernel parameter space: costs no registers)
+    const int *tape_z;          // z_c, z_k, z_e the tape was laid out with
 
     __device__ __forceinline__ uint4 philox(uint32_t agent, uint32_t phase, uint32_t block) const
     {
@@ -146,7 +146,7 @@ struct Draws {
     __device__ __forceinline__ double uniform(uint32_t phase, int agent) const
     {
         if (tape) {
-            uint32_t off = phase == PH_PRICE_C ? t.u_price_c : phase == PH_PRICE_K ? t.u_price_k : t.u_invest;
+            uint32_t off = phase == PH_PRICE_C ? tp->u_price_c : phase == PH_PRICE_K ? tp->u_price_k : tp->u_invest;
             return *reinterpret_cast<const double *>(tape + off + 8u * (uint32_t)agent);
         }
         uint4 w = philox((uint32_t)agent, phase, 0);
@@ -154,7 +154,7 @@ struct Draws {
     }
     __device__ __forceinline__ uint32_t fire_key(int worker) const
     {
-        if (tape) return *reinterpret_cast<const uint32_t *>(tape + t.fire_key + 4u * (uint32_t)worker);
+        if (tape) return *reinterpret_cast<const uint32_t *>(tape + tp->fire_key + 4u * (uint32_t)worker);
         return philox((uint32_t)worker, PH_FIRE, 0).x;
     }
     // z <= 8 distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
@@ -163,9 +163,9 @@ struct Draws {
     {
         if (tape) {
             uint32_t off; int zz;
-            if (phase == PH_JOB) { off = t.job_cand; zz = z_e; }
-            else if (phase == PH_CAP) { off = t.cap_cand; zz = z_k; }
-            else { off = t.goods_cand; zz = z_c; }
+            if (phase == PH_JOB) { off = tp->job_cand; zz = tape_z[2]; }
+            else if (phase == PH_CAP) { off = tp->cap_cand; zz = tape_z[1]; }
+            else { off = tp->goods_cand; zz = tape_z[0]; }
             const int *src = reinterpret_cast<const int *>(tape + off) + (size_t)agent * (size_t)zz;
 #pragma unroll
             for (int k = 0; k < ZM; ++k) out[k] = k < z ? src[k] : 0;
@@ -195,37 +195,49 @@ struct Draws {
     }
 };
 
-// visiting order of a market: tape permutation, or the keyed bijection of docs/MODEL.md 3.3
-struct Order {
+// visiting order of a market: tape permutation, or the keyed bijection of docs/MODEL.md 3.3.
+// The round keys live in shared memory (OrderKeys) and are re-read at every use: they are needed
+// once per 32 agents, and registers are what bounds how many economies are resident per SM.
+struct OrderKeys {
+    uint32_t m[4], a[4], mask, s, n, pad;
     const int *tape_order;
-    uint32_t m0, m1, m2, m3, a0, a1, a2, a3, mask;
-    int s, n;
-    __device__ __forceinline__ void init(const Draws &d, int market, int n_)
+};
+struct Order {
+    volatile OrderKeys *k;
+    __device__ __forceinline__ void init(const Draws &d, int market, int n, OrderKeys *keys, int lane)
     {
-        n = n_; tape_order = nullptr;
-        if (d.tape) {
-            uint32_t off = market == MKT_JOB ? d.t.job_order : market == MKT_CAP ? d.t.cap_order : d.t.goods_order;
-            tape_order = reinterpret_cast<const int *>(d.tape + off);
-            return;
+        k = keys;
+        if (lane == 0) {
+            keys->n = (uint32_t)n; keys->tape_order = nullptr;
+            if (d.tape) {
+                uint32_t off = market == MKT_JOB ? d.tp->job_order : market == MKT_CAP ? d.tp->cap_order : d.tp->goods_order;
+                keys->tape_order = reinterpret_cast<const int *>(d.tape + off);
+            } else {
+                uint4 w0 = d.philox((uint32_t)market, PH_ORDER, 0), w1 = d.philox((uint32_t)market, PH_ORDER, 1);
+                int b = 1;
+                while ((1u << b) < (uint32_t)n) ++b;
+                keys->mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+                keys->s = (uint32_t)(b / 2 > 0 ? b / 2 : 1);
+                keys->m[0] = w0.x | 1u; keys->m[1] = w0.y | 1u; keys->m[2] = w1.x | 1u; keys->m[3] = w1.y | 1u;
+                keys->a[0] = w0.z; keys->a[1] = w0.w; keys->a[2] = w1.z; keys->a[3] = w1.w;
+            }
         }
-        uint4 w0 = d.philox((uint32_t)market, PH_ORDER, 0), w1 = d.philox((uint32_t)market, PH_ORDER, 1);
-        int b = 1;
-        while ((1u << b) < (uint32_t)n) ++b;
-        mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-        s = b / 2 > 0 ? b / 2 : 1;
-        m0 = w0.x | 1u; m1 = w0.y | 1u; m2 = w1.x | 1u; m3 = w1.y | 1u;
-        a0 = w0.z; a1 = w0.w; a2 = w1.z; a3 = w1.w;
+        __syncwarp();
     }
     __device__ __forceinline__ int at(int pos) const
     {
-        if (tape_order) return tape_order[pos];
+        const int *to = k->tape_order;
+        if (to) return to[pos];
+        const uint32_t m0 = k->m[0], m1 = k->m[1], m2 = k->m[2], m3 = k->m[3];
+        const uint32_t a0 = k->a[0], a1 = k->a[1], a2 = k->a[2], a3 = k->a[3];
+        const uint32_t mask = k->mask, s = k->s, n = k->n;
         uint32_t x = (uint32_t)pos;
         do {
             x = (x * m0 + a0) & mask; x ^= x >> s;
             x = (x * m1 + a1) & mask; x ^= x >> s;
             x = (x * m2 + a2) & mask; x ^= x >> s;
             x = (x * m3 + a3) & mask; x ^= x >> s;
-        } while (x >= (uint32_t)n);
+        } while (x >= n);
         return (int)x;
     }
 };
@@ -259,14 +271,26 @@ __device__ __forceinline__ void sort_by_price(int (&cand)[ZM], double (&pr)[ZM],
 }
 
 // demand registered at a consumption-goods seller: 2^-40 fixed point, wrap-around add (MODEL.md 4.4)
-__device__ __forceinline__ unsigned long long fx_from(double d)
+__device__ __forceinline__ unsigned long long fx_from(double x)
 {
-    if (!(d < 4194304.0)) return 1ull << 62;
-    return (unsigned long long)__double2ll_rn(d * 1099511627776.0);
+    if (!(x < 4194304.0)) return 1ull << 62;
+    return (unsigned long long)__double2ll_rn(x * 1099511627776.0);
 }
 __device__ __forceinline__ double fx_to(unsigned long long a)
 {
     return (double)(long long)a * (1.0 / 1099511627776.0);
+}
+// 64-bit integer add on a shared-memory accumulator from two native 32-bit atomics (a 64-bit
+// shared atomicAdd compiles to a compare-and-swap spin loop).  Integer adds commute, and every
+// carry out of the low word is added to the high word exactly once, so the final value is exact.
+__device__ __forceinline__ void fx_add(unsigned long long *acc, unsigned long long x)
+{
+    unsigned *w = reinterpret_cast<unsigned *>(acc);
+    const unsigned lo = (unsigned)x;
+    unsigned hi = (unsigned)(x >> 32);
+    const unsigned old = atomicAdd(&w[0], lo);
+    hi += (old + lo < old) ? 1u : 0u;
+    if (hi) atomicAdd(&w[1], hi);
 }
 
 __device__ __forceinline__ int d2count(double x)

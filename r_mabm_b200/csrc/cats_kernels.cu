@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -52,27 +53,36 @@ struct KArgs {
     unsigned *status;
     double *stats;
     const unsigned char *tape;
+    int tape_z[3];
     int stop_phase;
     unsigned char *debug;
     long long *cycles;  // debug: [16] per-phase clock64 totals of block 0
 };
 
-// per-warp view of the working set
+// per-warp view of the working set.  Only two base pointers are kept: every section address is
+// base + a constant-bank offset, recomputed where it is used (registers are what bounds residency).
 struct Ctx {
-    unsigned char *sm;
-    unsigned char *blob;  // this economy's blob in global memory (Oc, C-firm rows, PA, perm live there)
+    unsigned char *sm;    // shared-memory working set
+    unsigned char *blob;  // this economy's blob in global memory (Oc, C-firm rows, cold K rows, PA, perm live there)
     const KArgs *a;
-    double *scal, *par;   // shared
-    int *Leff, *vac;      // shared (labour demand Ld == Leff + vac)
-    int *Oc;              // GLOBAL
-    double *PA, *perm;    // GLOBAL
-    double *mean;         // shared scratch: 8 doubles
-    int *misc;            // shared scratch ints
     int lane;
-    unsigned lt;          // lanes below this one
     long long b;          // economy index inside this launch
     int last;             // last phase id to execute (stop_phase or 99)
     Draws d;
+    __device__ __forceinline__ unsigned lt() const { return (1u << lane) - 1u; }   // lanes below this one
+    __device__ __forceinline__ double *scal() const { return reinterpret_cast<double *>(sm + a->L.o_scal); }
+    __device__ __forceinline__ double *par() const { return reinterpret_cast<double *>(sm + a->L.s_par); }
+    __device__ __forceinline__ int *Leff() const { return reinterpret_cast<int *>(sm + a->L.o_Leff); }
+    __device__ __forceinline__ int *vac() const { return reinterpret_cast<int *>(sm + a->L.s_vac); }   // Ld == Leff + vac
+    __device__ __forceinline__ int *misc() const { return reinterpret_cast<int *>(sm + a->L.s_misc); }
+    __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 32); }
+    __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 96); }
+    __device__ __forceinline__ int *Oc() const { return reinterpret_cast<int *>(blob + a->L.o_Oc); }          // GLOBAL
+    __device__ __forceinline__ double *PA() const { return reinterpret_cast<double *>(blob + a->L.o_PA); }    // GLOBAL
+    __device__ __forceinline__ double *perm() const { return reinterpret_cast<double *>(blob + a->L.o_perm); }  // GLOBAL
+    __device__ __forceinline__ int z_c() const { return (int)par()[P_z_c]; }
+    __device__ __forceinline__ int z_k() const { return (int)par()[P_z_k]; }
+    __device__ __forceinline__ int z_e() const { return (int)par()[P_z_e]; }
     __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + a->L.o_c + field * a->L.rowF); }  // GLOBAL
     // K-firm rows: hot ones (P, Yd, Q) are SHARED, the others GLOBAL; `field` is a compile-time constant
     __device__ __forceinline__ double *kf(int field) const
@@ -105,8 +115,8 @@ __device__ __forceinline__ void credit_one(const Ctx &c, double need, double b1,
                                            double A, double &interest_r, double &Ftot, double liquidity,
                                            int &Ld, int Leff, int &vac)
 {
-    const double theta = c.par[P_theta], mu = c.par[P_mu], r_f = c.par[P_r_f];
-    const double wb = c.scal[S_wb];
+    const double theta = c.par()[P_theta], mu = c.par()[P_mu], r_f = c.par()[P_r_f];
+    const double wb = c.scal()[S_wb];
     double B = need > 0.0 ? need : 0.0;
     double credit = 0.0;
     if (B > 0.0) {
@@ -115,10 +125,10 @@ __device__ __forceinline__ void credit_one(const Ctx &c, double need, double b1,
         double x = b1 + b2 * lev;
         double pr = 1.0 / (1.0 + det_exp(-x));
         double y = 1.0 + 1.0 / pr;
-        double pw = det_exp(y * c.par[P_log1mtheta]);
+        double pw = det_exp(y * c.par()[P_log1mtheta]);
         double Xi = (1.0 - pw) / theta;
         double rate = mu * ((1.0 + r_f / theta) / Xi - theta);
-        double maxL = (c.par[P_phi] * c.scal[S_bank_E] - pr * d0) / pr;
+        double maxL = (c.par()[P_phi] * c.scal()[S_bank_E] - pr * d0) / pr;
         if (!(maxL > 0.0)) maxL = 0.0;
         credit = B < maxL ? B : maxL;
         double d1 = d0 + credit;
@@ -141,8 +151,8 @@ __device__ void phase_firm_decisions(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int F = L.F, N = L.N, last = c.last;
-    const double alpha = c.par[P_alpha], q_adj = c.par[P_q_adj], p_adj = c.par[P_p_adj];
-    const double wb = c.scal[S_wb];
+    const double alpha = c.par()[P_alpha], q_adj = c.par()[P_q_adj], p_adj = c.par()[P_p_adj];
+    const double wb = c.scal()[S_wb];
     double accC = 0.0, accK = 0.0;  // det_sum partials of new credit
     for (int f = c.lane; f < F; f += 32) {
         double *De = c.cf(C_De), *P = c.cf(C_P);
@@ -151,7 +161,7 @@ __device__ void phase_firm_decisions(Ctx &c)
         const double prevDe = de, prevP = p;
         // phase 3: a3 firms_decide_price_quantity! (cats.py:363)
         {
-            double stock = Yprev - Yd, avg = c.scal[S_price];
+            double stock = Yprev - Yd, avg = c.scal()[S_price];
             double u = c.d.uniform(PH_PRICE_C, f);
             if (stock <= 0.0) {
                 if (p >= avg) de = Yprev + (-stock) * q_adj;
@@ -165,7 +175,7 @@ __device__ void phase_firm_decisions(Ctx &c)
         // phase 5: a5 firms_decide_investment! (cats.py:366)
         double kd = 0.0;
         if (last >= 5) {
-            const double Iprob = c.par[P_Iprob], barX = c.par[P_barX], eta = c.par[P_eta];
+            const double Iprob = c.par()[P_Iprob], barX = c.par()[P_barX], eta = c.par()[P_eta];
             double u = c.d.uniform(PH_INVEST, f);
             if (u < Iprob) {
                 double K = c.cf(C_K)[f];
@@ -182,7 +192,7 @@ __device__ void phase_firm_decisions(Ctx &c)
             const bool real = c.a->mask ? (c.a->mask[ai] != 0) : true;
             if (real) {
                 double a0 = c.a->actions[2 * ai], a1 = c.a->actions[2 * ai + 1];
-                double base = (c.a->flags & CATS_FLAG_AVG_PRICE) ? c.scal[S_price] : prevP;
+                double base = (c.a->flags & CATS_FLAG_AVG_PRICE) ? c.scal()[S_price] : prevP;
                 if (c.a->flags & CATS_FLAG_LOG) {
                     de = det_exp(det_log(prevDe + 1e-8) + a0);
                     p = det_exp(det_log(base + 1e-8) + a1);
@@ -197,20 +207,20 @@ __device__ void phase_firm_decisions(Ctx &c)
         // phase 7: a7 firms_decide_labour! (cats.py:373)
         if (last >= 7) {
             double aa = ceil(de / alpha);
-            double bb = ceil((c.cf(C_K)[f] * c.par[P_k]) / alpha);
+            double bb = ceil((c.cf(C_K)[f] * c.par()[P_k]) / alpha);
             int Ld = d2count(aa < bb ? aa : bb);
-            int vac = Ld - c.Leff[f];
+            int vac = Ld - c.Leff()[f];
             // phase 9: a8 firms_get_credit! (cats.py:376)
             if (last >= 9) {
                 double liq = c.cf(C_liquidity)[f];
-                double need = (wb * (double)Ld + kd * c.scal[S_price_k]) - liq;
+                double need = (wb * (double)Ld + kd * c.scal()[S_price_k]) - liq;
                 double deb = c.cf(C_deb)[f], ir = c.cf(C_interest_r)[f], Ftot;
-                credit_one(c, need, c.par[P_b1], c.par[P_b2], deb, c.cf(C_A)[f], ir, Ftot, liq, Ld,
-                           c.Leff[f], vac);
+                credit_one(c, need, c.par()[P_b1], c.par()[P_b2], deb, c.cf(C_A)[f], ir, Ftot, liq, Ld,
+                           c.Leff()[f], vac);
                 c.cf(C_deb)[f] = deb; c.cf(C_interest_r)[f] = ir; c.at(L.s_cFtot)[f] = Ftot;
                 accC = accC + Ftot;
             }
-            c.vac[f] = vac;
+            c.vac()[f] = vac;
         }
     }
     for (int i = c.lane; i < N; i += 32) {
@@ -219,7 +229,7 @@ __device__ void phase_firm_decisions(Ctx &c)
         double p = P[i], de = De[i];
         // phase 4: a4 firms_decide_price_quantity! for K-firms (cats.py:364)
         if (last >= 4) {
-            double stock = avail - Yd, avg = c.scal[S_price_k];
+            double stock = avail - Yd, avg = c.scal()[S_price_k];
             double u = c.d.uniform(PH_PRICE_K, i);
             if (stock <= 0.0) {
                 if (p >= avg) de = Yprev + (-stock) * q_adj;
@@ -234,27 +244,27 @@ __device__ void phase_firm_decisions(Ctx &c)
         // phase 8: a7 firms_decide_labour! for K-firms (cats.py:374)
         if (last >= 8) {
             int Ld = d2count(ceil(de / alpha));
-            int vac = Ld - c.Leff[F + i];
+            int vac = Ld - c.Leff()[F + i];
             // phase 10: a8 firms_get_credit! for K-firms (cats.py:377)
             if (last >= 10) {
                 double liq = c.kf(K_liquidity)[i];
                 double need = wb * (double)Ld - liq;
                 double deb = c.kf(K_deb)[i], ir = c.kf(K_interest_r)[i], Ftot;
-                credit_one(c, need, c.par[P_b_k1], c.par[P_b_k2], deb, c.kf(K_A)[i], ir, Ftot, liq, Ld,
-                           c.Leff[F + i], vac);
+                credit_one(c, need, c.par()[P_b_k1], c.par()[P_b_k2], deb, c.kf(K_A)[i], ir, Ftot, liq, Ld,
+                           c.Leff()[F + i], vac);
                 c.kf(K_deb)[i] = deb; c.kf(K_interest_r)[i] = ir; c.at(L.s_kFtot)[i] = Ftot;
                 accK = accK + Ftot;
             }
-            c.vac[F + i] = vac;
+            c.vac()[F + i] = vac;
         }
     }
     // bank loan stock: += det_sum(new credit), C-firms then K-firms
     if (last >= 9) {
         accC = bfly(accC); accK = bfly(accK);
         if (c.lane == 0) {
-            double loans = c.scal[S_bank_loans] + accC;
+            double loans = c.scal()[S_bank_loans] + accC;
             if (last >= 10) loans = loans + accK;
-            c.scal[S_bank_loans] = loans;
+            c.scal()[S_bank_loans] = loans;
         }
     }
     __syncwarp();
@@ -270,12 +280,12 @@ __device__ void phase_fire(Ctx &c, int limit)
     const int W = L.W, lane = c.lane;
     int *ic = c.iat(L.s_ic);    // per firm: pooled head-count (low 16 bits) | pool cursor (high 16 bits)
     bool over = false;
-    for (int f = lane; f < limit; f += 32) { over |= c.vac[f] < 0; ic[f] = 0; }
+    for (int f = lane; f < limit; f += 32) { over |= c.vac()[f] < 0; ic[f] = 0; }
     if (!__any_sync(FULL, over)) return;
     __syncwarp();
     for (int w = lane; w < W; w += 32) {
-        int f = c.Oc[w];
-        if (f >= 0 && f < limit && c.vac[f] < 0) atomicAdd(&ic[f], 1);
+        int f = c.Oc()[w];
+        if (f >= 0 && f < limit && c.vac()[f] < 0) atomicAdd(&ic[f], 1);
     }
     __syncwarp();
     const int cap = L.U_bytes / 8;
@@ -305,11 +315,11 @@ __device__ void phase_fire(Ctx &c, int limit)
         if (f1 == f0) {
             // one firm larger than the pool: s arg-min selections over all workers (slow, rare)
             const int f = f0;
-            const int s = -c.vac[f];
+            const int s = -c.vac()[f];
             for (int r = 0; r < s; ++r) {
                 unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
                 for (int w = lane; w < W; w += 32) {
-                    if (c.Oc[w] == f) {
+                    if (c.Oc()[w] == f) {
                         unsigned key = c.d.fire_key(w);
                         if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
                     }
@@ -321,10 +331,10 @@ __device__ void phase_fire(Ctx &c, int limit)
                     if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
                 }
                 if (bw == 0x7fffffff) break;
-                if (lane == 0) c.Oc[bw] = -1;
+                if (lane == 0) c.Oc()[bw] = -1;
                 __syncwarp();
             }
-            if (lane == 0) { c.Leff[f] = c.Leff[f] + c.vac[f]; c.vac[f] = 0; }
+            if (lane == 0) { c.Leff()[f] = c.Leff()[f] + c.vac()[f]; c.vac()[f] = 0; }
             __syncwarp();
             f0 = f + 1;
             continue;
@@ -332,8 +342,8 @@ __device__ void phase_fire(Ctx &c, int limit)
         const int total = base;
         if (total > 0) {
             for (int w = lane; w < W; w += 32) {
-                int f = c.Oc[w];
-                if (f >= f0 && f < f1 && c.vac[f] < 0) {
+                int f = c.Oc()[w];
+                if (f >= f0 && f < f1 && c.vac()[f] < 0) {
                     int slot = atomicAdd(&ic[f], 0x10000) >> 16;
                     pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
                 }
@@ -341,7 +351,7 @@ __device__ void phase_fire(Ctx &c, int limit)
             __syncwarp();
             for (int i = lane; i < total; i += 32) {
                 const int w = pool_w[i]; const unsigned key = pool_k[i];
-                const int f = c.Oc[w];
+                const int f = c.Oc()[w];
                 const int v = ic[f];
                 const int end = v >> 16, beg = end - (v & 0xffff);
                 int rank = 0;
@@ -349,12 +359,12 @@ __device__ void phase_fire(Ctx &c, int limit)
                     const unsigned kj = pool_k[j]; const int wj = pool_w[j];
                     rank += (kj < key || (kj == key && wj < w)) ? 1 : 0;
                 }
-                if (rank < -c.vac[f]) c.Oc[w] = -1;
+                if (rank < -c.vac()[f]) c.Oc()[w] = -1;
             }
             __syncwarp();
         }
         for (int f = f0 + lane; f < f1; f += 32)
-            if (c.vac[f] < 0) { c.Leff[f] = c.Leff[f] + c.vac[f]; c.vac[f] = 0; }
+            if (c.vac()[f] < 0) { c.Leff()[f] = c.Leff()[f] + c.vac()[f]; c.vac()[f] = 0; }
         __syncwarp();
         f0 = f1;
     }
@@ -370,8 +380,8 @@ __device__ void phase_job_search(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int W = L.W, nf = L.F + L.N, lane = c.lane;
-    const int z = c.d.z_e < nf ? c.d.z_e : nf;
-    Order ord; ord.init(c.d, MKT_JOB, W);
+    const int z = c.z_e() < nf ? c.z_e() : nf;
+    Order ord; ord.init(c.d, MKT_JOB, W, c.okeys(), lane);
     unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
     int total = 0;
     for (int base = 0; base < W; base += 128) {
@@ -382,17 +392,17 @@ __device__ void phase_job_search(Ctx &c)
             w[q] = pos < W ? ord.at(pos) : -1;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) oc[q] = w[q] >= 0 ? c.Oc[w[q]] : 0;
+        for (int q = 0; q < 4; ++q) oc[q] = w[q] >= 0 ? c.Oc()[w[q]] : 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const bool un = oc[q] < 0;
             const unsigned bal = __ballot_sync(FULL, un);
-            if (un) seekers[total + __popc(bal & c.lt)] = (unsigned short)w[q];
+            if (un) seekers[total + __popc(bal & c.lt())] = (unsigned short)w[q];
             total += __popc(bal);
         }
     }
     __syncwarp();
-    const unsigned lt = c.lt;
+    const unsigned lt = c.lt();
     for (int base = 0; base < total; base += 32) {
         const int idx = base + lane;
         int w = -1;
@@ -405,18 +415,18 @@ __device__ void phase_job_search(Ctx &c)
             if (mine) {
 #pragma unroll
                 for (int k = 0; k < ZM; ++k)
-                    if (k < z && pick < 0 && c.vac[cand[k]] > 0) pick = cand[k];
+                    if (k < z && pick < 0 && c.vac()[cand[k]] > 0) pick = cand[k];
             }
             const bool has = mine && pick >= 0;
             const unsigned peers = __match_any_sync(FULL, has ? pick : -1 - lane);
-            const bool ok = !has || __popc(peers & lt) < c.vac[pick];
+            const bool ok = !has || __popc(peers & lt) < c.vac()[pick];
             const unsigned badm = __ballot_sync(FULL, mine && !ok);
             const unsigned commit = badm ? (pending & ((1u << (__ffs(badm) - 1)) - 1u)) : pending;
             __syncwarp();
             if (has && ((commit >> lane) & 1u)) {
-                c.Oc[w] = pick;
+                c.Oc()[w] = pick;
                 const unsigned grp = peers & commit;
-                if ((grp & lt) == 0) { int n = __popc(grp); c.vac[pick] -= n; c.Leff[pick] += n; }
+                if ((grp & lt) == 0) { int n = __popc(grp); c.vac()[pick] -= n; c.Leff()[pick] += n; }
             }
             pending &= ~commit;
             __syncwarp();
@@ -434,11 +444,11 @@ __device__ void phase_produce(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int F = L.F, N = L.N, last = c.last;
-    const double alpha = c.par[P_alpha], k = c.par[P_k], eta = c.par[P_eta], theta = c.par[P_theta];
-    const double wb = c.scal[S_wb], pk = c.scal[S_price_k];
+    const double alpha = c.par()[P_alpha], k = c.par()[P_k], eta = c.par()[P_eta], theta = c.par()[P_theta];
+    const double wb = c.scal()[S_wb], pk = c.scal()[S_price_k];
     MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
     for (int f = c.lane; f < F; f += 32) {
-        double Leff = (double)c.Leff[f];
+        double Leff = (double)c.Leff()[f];
         double cap_l = Leff * alpha, cap_k = c.cf(C_K)[f] * k;
         double Yp = cap_l < cap_k ? cap_l : cap_k;
         double De = c.cf(C_De)[f];
@@ -458,7 +468,7 @@ __device__ void phase_produce(Ctx &c)
     }
     if (last >= 15) {
         for (int i = c.lane; i < N; i += 32) {
-            double Leff = (double)c.Leff[F + i];
+            double Leff = (double)c.Leff()[F + i];
             double want = c.kf(K_De)[i];
             double cap_l = Leff * alpha;
             double Y = want < cap_l ? want : cap_l;
@@ -486,8 +496,8 @@ __device__ void phase_capital_market(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int F = L.F, N = L.N, lane = c.lane;
-    const int z = c.d.z_k < N ? c.d.z_k : N;
-    Order ord; ord.init(c.d, MKT_CAP, F);
+    const int z = c.z_k() < N ? c.z_k() : N;
+    Order ord; ord.init(c.d, MKT_CAP, F, c.okeys(), lane);
     double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.s_kYstock);
     double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
     double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
@@ -498,7 +508,7 @@ __device__ void phase_capital_market(Ctx &c)
         int f = -1; bool act = false;
         if (pos < F) { f = ord.at(pos); act = Kdem[f] > 0.0; }
         const unsigned bal = __ballot_sync(FULL, act);
-        if (act) buyers[total + __popc(bal & c.lt)] = f;
+        if (act) buyers[total + __popc(bal & c.lt())] = f;
         total += __popc(bal);
     }
     __syncwarp();
@@ -566,20 +576,20 @@ __device__ void phase_gov_income(Ctx &c)
 {
     const Layout &L = c.a->L;
     int n = 0;
-    for (int i = c.lane; i < L.F + L.N; i += 32) n += c.Leff[i];
+    for (int i = c.lane; i < L.F + L.N; i += 32) n += c.Leff()[i];
     n = bfly_i(n);
     if (c.lane == 0) {
-        double sub = c.par[P_subsidy] * c.scal[S_wb];
-        if (c.par[P_maastricht] > 0.0 && c.scal[S_deficitGDP] > c.par[P_target_deficit]) {
-            double scale = 1.0 - c.par[P_maastricht] * (c.scal[S_deficitGDP] - c.par[P_target_deficit]);
+        double sub = c.par()[P_subsidy] * c.scal()[S_wb];
+        if (c.par()[P_maastricht] > 0.0 && c.scal()[S_deficitGDP] > c.par()[P_target_deficit]) {
+            double scale = 1.0 - c.par()[P_maastricht] * (c.scal()[S_deficitGDP] - c.par()[P_target_deficit]);
             if (!(scale > 0.0)) scale = 0.0;
             sub = sub * scale;
         }
-        c.scal[S_gov_subsidy_level] = sub;
+        c.scal()[S_gov_subsidy_level] = sub;
         if (c.last >= 18) {
-            const double wb = c.scal[S_wb], tax = c.par[P_tax_rate];
-            c.scal[S_gov_TA] = c.scal[S_gov_TA] + (wb * tax) * (double)n;
-            c.scal[S_gov_G] = c.scal[S_gov_G] + sub * (double)(L.W - n);
+            const double wb = c.scal()[S_wb], tax = c.par()[P_tax_rate];
+            c.scal()[S_gov_TA] = c.scal()[S_gov_TA] + (wb * tax) * (double)n;
+            c.scal()[S_gov_G] = c.scal()[S_gov_G] + sub * (double)(L.W - n);
         }
     }
     __syncwarp();
@@ -589,12 +599,12 @@ __device__ void phase_gov_income(Ctx &c)
 __device__ void phase_households_only(Ctx &c)
 {
     const Layout &L = c.a->L;
-    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
-    const double xi = c.par[P_xi], chi = c.par[P_chi];
+    const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
+    const double xi = c.par()[P_xi], chi = c.par()[P_chi];
     for (int h = c.lane; h < L.H; h += 32) {
-        double pa = c.PA[h], pm = c.perm[h];
+        double pa = c.PA()[h], pm = c.perm()[h];
         double inc;
-        if (h < L.W) { inc = c.Oc[h] >= 0 ? wb * (1.0 - c.par[P_tax_rate]) : sub; pa = pa + inc; }
+        if (h < L.W) { inc = c.Oc()[h] >= 0 ? wb * (1.0 - c.par()[P_tax_rate]) : sub; pa = pa + inc; }
         else inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
         if (c.last >= 19) {
             double ir = inc / price;
@@ -605,7 +615,7 @@ __device__ void phase_households_only(Ctx &c)
             if (!(b > 0.0)) b = 0.0;
             pa = pa - b;
         }
-        c.PA[h] = pa; c.perm[h] = pm;
+        c.PA()[h] = pa; c.perm()[h] = pm;
     }
     __syncwarp();
 }
@@ -626,15 +636,21 @@ __device__ void phase_goods_market(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int W = L.W, F = L.F, H = L.H, lane = c.lane;
-    const unsigned lt = c.lt;
-    const int z = c.d.z_c < F ? c.d.z_c : F;
+    const unsigned lt = c.lt();
+    const int z = c.z_c() < F ? c.z_c() : F;
     MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
-    Order ord; ord.init(c.d, MKT_GOODS, H);
-    const double wb = c.scal[S_wb], sub = c.scal[S_gov_subsidy_level], price = c.scal[S_price];
-    const double xi = c.par[P_xi], chi = c.par[P_chi];
-    const double net = wb * (1.0 - c.par[P_tax_rate]);
-    const double ir_emp = net / price, ir_un = sub / price;
-    const double omxi = 1.0 - xi;
+    Order ord; ord.init(c.d, MKT_GOODS, H, c.okeys(), lane);
+    // market constants: computed once, parked in shared memory and re-read per chunk (registers)
+    enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
+    volatile double *gk = c.gk();
+    if (lane == 0) {
+        const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
+        const double xi = c.par()[P_xi];
+        const double net = wb * (1.0 - c.par()[P_tax_rate]);
+        gk[G_net] = net; gk[G_sub] = sub; gk[G_ir_emp] = net / price; gk[G_ir_un] = sub / price;
+        gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = 1.0 / price;
+    }
+    __syncwarp();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int nch = (H + 31) / 32;
 
@@ -645,8 +661,8 @@ __device__ void phase_goods_market(Ctx &c)
         h_n = -1; oc_n = -1; pa_n = 0.0; pm_n = 0.0; dinc_n = 0.0;
         if (pos < H) {
             const int h = ord.at(pos);
-            h_n = h; pa_n = c.PA[h]; pm_n = c.perm[h];
-            if (h < W) oc_n = c.Oc[h];
+            h_n = h; pa_n = c.PA()[h]; pm_n = c.perm()[h];
+            if (h < W) oc_n = c.Oc()[h];
             else if (h < W + F) dinc_n = c.cf(C_div_income)[h - W];
             else dinc_n = c.kf(K_div_income)[h - W - F];
         }
@@ -659,17 +675,19 @@ __device__ void phase_goods_market(Ctx &c)
         if (ch + 1 < nch) fetch(ch + 1);
         // a14 + a15: income, permanent income, consumption budget
         double b = 0.0;
+        const double rpavg = gk[G_rpavg];
         if (h >= 0) {
+            const double price = gk[G_price];
             double ir;
-            if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? net : sub); ir = emp ? ir_emp : ir_un; }
+            if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
             else ir = dinc / price;
-            pm = pm * xi + omxi * ir;
-            const double target = pm + (chi * pa) / price;
+            pm = pm * gk[G_xi] + gk[G_omxi] * ir;
+            const double target = pm + (gk[G_chi] * pa) / price;
             b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
             pa = pa - b;
-            c.perm[h] = pm;
+            c.perm()[h] = pm;
         }
         // a16: candidates, sorted by price, packed 16 bits each
         unsigned long long cp0 = 0ull, cp1 = 0ull;
@@ -689,8 +707,10 @@ __device__ void phase_goods_market(Ctx &c)
         int nrem = b > 0.0 ? z : 0, term = -1;
         double p_t = 1.0, d_t = 0.0;
         bool dirty = b > 0.0;
+        unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
         while (pend) {
             // ---- walk: dirty lanes register demand seller by seller until one has stock
+            bool moved = false;
             while (__any_sync(FULL, dirty)) {
                 if (dirty) {
                     if (nrem == 0) { term = -1; dirty = false; }   // every candidate is sold out
@@ -699,12 +719,12 @@ __device__ void phase_goods_market(Ctx &c)
                         cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
                         MktRec *r = &mkt[cnd];
                         const double2 yp = *reinterpret_cast<const double2 *>(r);   // stock, price
-                        const double d = b / yp.y;
-                        atomicAdd(&r->acc, fx_from(d));
-                        if (yp.x > 0.0) { term = cnd; p_t = yp.y; d_t = d; dirty = false; }
+                        fx_add(&r->acc, xb);
+                        if (yp.x > 0.0) { term = cnd; p_t = yp.y; dirty = false; moved = true; }
                     }
                 }
             }
+            if (moved) d_t = b / p_t;
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
             const bool mine = (pend >> lane) & 1u;
             const bool has = mine && term >= 0;
@@ -739,6 +759,7 @@ __device__ void phase_goods_market(Ctx &c)
                         term = -1;
                         dirty = b > 0.0;
                         done = !dirty;
+                        xb = fx_from(b * rpavg);
                     }
                     if (lastp) { r->ys = ys; r->q = q; }
                 }
@@ -748,12 +769,12 @@ __device__ void phase_goods_market(Ctx &c)
             pend &= ~__ballot_sync(FULL, done);
             __syncwarp();
         }
-        if (h >= 0) c.PA[h] = pa + b;   // involuntary saving
+        if (h >= 0) c.PA()[h] = pa + b;   // involuntary saving
     }
     // close: unpack the seller records
     {
         double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
-        for (int f = lane; f < F; f += 32) { const MktRec r = mkt[f]; Yd[f] = fx_to(r.acc); Q[f] = r.q; }
+        for (int f = lane; f < F; f += 32) { const MktRec r = mkt[f]; Yd[f] = (fx_to(r.acc) * gk[G_price]) / r.p; Q[f] = r.q; }
     }
     __syncwarp();
 }
@@ -763,8 +784,8 @@ __device__ void phase_accounting(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int W = L.W, F = L.F, N = L.N, last = c.last;
-    const double delta = c.par[P_delta], eta = c.par[P_eta], k = c.par[P_k], theta = c.par[P_theta];
-    const double divs = c.par[P_div], taxd = c.par[P_tax_rate_d];
+    const double delta = c.par()[P_delta], eta = c.par()[P_eta], k = c.par()[P_k], theta = c.par()[P_theta];
+    const double divs = c.par()[P_div], taxd = c.par()[P_tax_rate_d];
     const MktRec *mkt = reinterpret_cast<const MktRec *>(c.sm + L.s_U);
     double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;   // det_sum partials
     for (int f = c.lane; f < F; f += 32) {
@@ -791,7 +812,7 @@ __device__ void phase_accounting(Ctx &c)
             liq = liq - dvd; A = A - dvd;
             net = dvd * (1.0 - taxd);
             dt = dvd - net;
-            c.PA[W + f] = c.PA[W + f] + net;
+            c.PA()[W + f] = c.PA()[W + f] + net;
         }
         c.cf(C_div_income)[f] = net;
         c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;
@@ -800,7 +821,7 @@ __device__ void phase_accounting(Ctx &c)
     if (last >= 22) {
         for (int i = c.lane; i < N; i += 32) {
             double RIC = c.kf(K_P)[i] * c.kf(K_Q)[i];
-            c.kf(K_inv)[i] = (1.0 - c.par[P_inventory_depreciation]) * c.at(L.s_kYstock)[i];
+            c.kf(K_inv)[i] = (1.0 - c.par()[P_inventory_depreciation]) * c.at(L.s_kYstock)[i];
             double wages = c.kf(K_wages)[i], interests = c.kf(K_interests)[i];
             double deb = c.kf(K_deb)[i];
             double in = theta * deb;
@@ -814,7 +835,7 @@ __device__ void phase_accounting(Ctx &c)
                 liq = liq - dvd; A = A - dvd;
                 net = dvd * (1.0 - taxd);
                 dt = dvd - net;
-                c.PA[W + F + i] = c.PA[W + F + i] + net;
+                c.PA()[W + F + i] = c.PA()[W + F + i] + net;
             }
             c.kf(K_div_income)[i] = net;
             c.kf(K_liquidity)[i] = liq; c.kf(K_A)[i] = A;
@@ -825,11 +846,11 @@ __device__ void phase_accounting(Ctx &c)
     s_in = bfly(s_in); s_int = bfly(s_int); s_dt = bfly(s_dt);
     k_in = bfly(k_in); k_int = bfly(k_int); k_dt = bfly(k_dt);
     if (c.lane == 0) {
-        double loans = c.scal[S_bank_loans] - s_in;
-        double ii = c.scal[S_bank_interest_income] + s_int;
-        double ta = c.scal[S_gov_TA] + s_dt;
+        double loans = c.scal()[S_bank_loans] - s_in;
+        double ii = c.scal()[S_bank_interest_income] + s_int;
+        double ta = c.scal()[S_gov_TA] + s_dt;
         if (last >= 22) { loans = loans - k_in; ii = ii + k_int; ta = ta + k_dt; }
-        c.scal[S_bank_loans] = loans; c.scal[S_bank_interest_income] = ii; c.scal[S_gov_TA] = ta;
+        c.scal()[S_bank_loans] = loans; c.scal()[S_bank_interest_income] = ii; c.scal()[S_gov_TA] = ta;
     }
     __syncwarp();
 }
@@ -854,17 +875,17 @@ __device__ void phase_reward(Ctx &c)
         for (int i = c.lane; i < nA; i += 32) a.reward[c.b * nA + i] = (P[i] * Q[i]) / total;
         return;
     }
-    const double eta = c.par[P_eta], k = c.par[P_k];
+    const double eta = c.par()[P_eta], k = c.par()[P_k];
     for (int i = c.lane; i < nA; i += 32) {
         double dep = (eta * c.cf(C_Y_prev)[i]) / k;
         double den = (c.cf(C_K)[i] + dep) - c.cf(C_investment)[i];
         double dv;
-        if (den == 0.0) { dv = 0.0; atomicOr(&c.misc[M_STATUS], (int)CATS_STATUS_DEPVAL_DIV0); }
+        if (den == 0.0) { dv = 0.0; atomicOr(&c.misc()[M_STATUS], (int)CATS_STATUS_DEPVAL_DIV0); }
         else dv = (dep * c.cf(C_capital_value)[i]) / den;
         double RIC = P[i] * Q[i];
         double profits = ((RIC - c.cf(C_wages)[i]) - c.cf(C_interests)[i]) - dv;
-        profits = (profits * c.scal[S_init_price]) / c.scal[S_price];
-        if (profits != profits) { profits = 0.0; atomicOr(&c.misc[M_STATUS], (int)CATS_STATUS_PROFIT_NAN); }
+        profits = (profits * c.scal()[S_init_price]) / c.scal()[S_price];
+        if (profits != profits) { profits = 0.0; atomicOr(&c.misc()[M_STATUS], (int)CATS_STATUS_PROFIT_NAN); }
         if (c.cf(C_A)[i] <= 0.0) profits = a.bankruptcy_reward;
         a.reward[c.b * nA + i] = profits;
     }
@@ -882,18 +903,18 @@ __device__ void phase_tracking(Ctx &c)
     for (int f = c.lane; f < F; f += 32) {
         const double p = cP[f], q = cQ[f];
         sQ = sQ + q; sPQ = sPQ + p * q; sP = sP + p; sY = sY + cY[f]; sK = sK + cK[f];
-        nL += c.Leff[f];
+        nL += c.Leff()[f];
     }
     for (int i = c.lane; i < N; i += 32) {
         const double p = c.kf(K_P)[i], q = c.kf(K_Q)[i];
         sQk = sQk + q; sPQk = sPQk + p * q; sYk = sYk + c.kf(K_Y_prev)[i];
-        nL += c.Leff[F + i];
+        nL += c.Leff()[F + i];
     }
     sQ = bfly(sQ); sPQ = bfly(sPQ); sP = bfly(sP); sY = bfly(sY); sK = bfly(sK);
     sQk = bfly(sQk); sPQk = bfly(sPQk); sYk = bfly(sYk);
     nL = bfly_i(nL);
     if (c.lane == 0) {
-        double *s = c.scal;
+        double *s = c.scal();
         double price_prev = s[S_price];
         double price = sQ > 0.0 ? sPQ / sQ : sP / (double)F;
         double price_k = sQk > 0.0 ? sPQk / sQk : s[S_price_k];
@@ -915,7 +936,7 @@ __device__ void phase_bankrupt(Ctx &c)
 {
     const Layout &L = c.a->L;
     const int W = L.W, F = L.F, N = L.N;
-    const double thr = c.par[P_E_threshold_scale] * c.scal[S_price];
+    const double thr = c.par()[P_E_threshold_scale] * c.scal()[S_price];
     unsigned char *bad = c.sm + L.s_bad;
     // masked det_sums over the survivors / the defaulters, and survivor counts
     double cK = 0.0, cL = 0.0, cP = 0.0, cY = 0.0, cLoss = 0.0, cDeb = 0.0;
@@ -953,19 +974,19 @@ __device__ void phase_bankrupt(Ctx &c)
     cK = bfly(cK); cL = bfly(cL); cP = bfly(cP); cY = bfly(cY); cLoss = bfly(cLoss); cDeb = bfly(cDeb);
     kL = bfly(kL); kP = bfly(kP); kY = bfly(kY); kLoss = bfly(kLoss); kDeb = bfly(kDeb);
     nsC = bfly_i(nsC); nsK = bfly_i(nsK);
-    double mK = 10.0, mL = 0.0, mP = c.scal[S_price], mY = c.par[P_alpha];
+    double mK = 10.0, mL = 0.0, mP = c.scal()[S_price], mY = c.par()[P_alpha];
     if (nsC > 0) { mK = cK / (double)nsC; mL = cL / (double)nsC; mP = cP / (double)nsC; mY = cY / (double)nsC; }
-    double mLk = 0.0, mPk = c.scal[S_price_k], mYk = c.par[P_alpha];
+    double mLk = 0.0, mPk = c.scal()[S_price_k], mYk = c.par()[P_alpha];
     if (nsK > 0) { mLk = kL / (double)nsK; mPk = kP / (double)nsK; mYk = kY / (double)nsK; }
-    const double price_k = c.scal[S_price_k];
+    const double price_k = c.scal()[S_price_k];
     __syncwarp();
     if (c.lane == 0) {
-        double bd = c.scal[S_bank_bad_debt] + cLoss;
-        double loans = c.scal[S_bank_loans] - cDeb;
+        double bd = c.scal()[S_bank_bad_debt] + cLoss;
+        double loans = c.scal()[S_bank_loans] - cDeb;
         bd = bd + kLoss;
         loans = loans - kDeb;
-        c.scal[S_bank_bad_debt] = bd; c.scal[S_bank_loans] = loans;
-        c.scal[S_bankruptcy_rate] = (double)((F - nsC) + (N - nsK)) / (double)(F + N);
+        c.scal()[S_bank_bad_debt] = bd; c.scal()[S_bank_loans] = loans;
+        c.scal()[S_bankruptcy_rate] = (double)((F - nsC) + (N - nsK)) / (double)(F + N);
     }
     const int nbad = (F - nsC) + (N - nsK);
     if (nbad > 0) {
@@ -973,35 +994,35 @@ __device__ void phase_bankrupt(Ctx &c)
             if (!bad[f]) continue;
             const int ow = W + f;
             double inj = mL > 0.0 ? mL : 0.0;
-            double pa = c.PA[ow];
+            double pa = c.PA()[ow];
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
-            c.PA[ow] = pa - inj;
+            c.PA()[ow] = pa - inj;
             double cv = mK * price_k;
             c.cf(C_liquidity)[f] = inj; c.cf(C_K)[f] = mK; c.cf(C_capital_value)[f] = cv;
             c.cf(C_A)[f] = inj + cv; c.cf(C_deb)[f] = 0.0; c.cf(C_P)[f] = mP;
             c.cf(C_Y_prev)[f] = mY; c.cf(C_Yd)[f] = mY; c.cf(C_De)[f] = mY;
-            c.cf(C_barYK)[f] = mY / c.par[P_k]; c.cf(C_interest_r)[f] = c.par[P_r_f];
+            c.cf(C_barYK)[f] = mY / c.par()[P_k]; c.cf(C_interest_r)[f] = c.par()[P_r_f];
             c.cf(C_Q)[f] = 0.0; c.cf(C_investment)[f] = 0.0; c.cf(C_wages)[f] = 0.0;
             c.cf(C_interests)[f] = 0.0; c.cf(C_div_income)[f] = 0.0;
-            c.Leff[f] = 0;
+            c.Leff()[f] = 0;
         }
         for (int i = c.lane; i < N; i += 32) {
             if (!bad[F + i]) continue;
             const int ow = W + F + i;
             double inj = mLk > 0.0 ? mLk : 0.0;
-            double pa = c.PA[ow];
+            double pa = c.PA()[ow];
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
-            c.PA[ow] = pa - inj;
+            c.PA()[ow] = pa - inj;
             c.kf(K_liquidity)[i] = inj; c.kf(K_A)[i] = inj; c.kf(K_deb)[i] = 0.0;
             c.kf(K_P)[i] = mPk; c.kf(K_Y_prev)[i] = mYk; c.kf(K_Yd)[i] = mYk; c.kf(K_Yavail)[i] = mYk;
-            c.kf(K_De)[i] = mYk; c.kf(K_inv)[i] = 0.0; c.kf(K_interest_r)[i] = c.par[P_r_f];
+            c.kf(K_De)[i] = mYk; c.kf(K_inv)[i] = 0.0; c.kf(K_interest_r)[i] = c.par()[P_r_f];
             c.kf(K_Q)[i] = 0.0; c.kf(K_wages)[i] = 0.0; c.kf(K_interests)[i] = 0.0;
             c.kf(K_div_income)[i] = 0.0;
-            c.Leff[F + i] = 0;
+            c.Leff()[F + i] = 0;
         }
-        for (int w = c.lane; w < W; w += 32) { int o = c.Oc[w]; if (o >= 0 && bad[o]) c.Oc[w] = -1; }
+        for (int w = c.lane; w < W; w += 32) { int o = c.Oc()[w]; if (o >= 0 && bad[o]) c.Oc()[w] = -1; }
     }
     __syncwarp();
     {
@@ -1009,7 +1030,7 @@ __device__ void phase_bankrupt(Ctx &c)
         double s = 0.0;
         for (int f = c.lane; f < F; f += 32) s = s + A[f];
         s = bfly(s);
-        if (c.lane == 0) c.scal[S_terminated] = s == 0.0 ? 1.0 : 0.0;
+        if (c.lane == 0) c.scal()[S_terminated] = s == 0.0 ? 1.0 : 0.0;
     }
     __syncwarp();
 }
@@ -1021,10 +1042,10 @@ __device__ void phase_closing(Ctx &c)
     const int last = c.last;
     double share = 0.0;
     if (c.lane == 0) {
-        double *s = c.scal;
+        double *s = c.scal();
         double gross = (s[S_bank_interest_income] + s[S_gov_r_b] * s[S_gov_bonds]) - s[S_bank_bad_debt];
         double dB = 0.0;
-        if (gross > 0.0 && s[S_bank_E] > 0.0) dB = c.par[P_div] * gross;
+        if (gross > 0.0 && s[S_bank_E] > 0.0) dB = c.par()[P_div] * gross;
         s[S_bank_E] = s[S_bank_E] + (gross - dB);
         s[S_dividendsB] = dB; s[S_profitsB] = gross;
         share = dB > 0.0 ? dB / (double)(L.F + L.N) : 0.0;
@@ -1036,15 +1057,15 @@ __device__ void phase_closing(Ctx &c)
             s[S_deficitGDP] = s[S_Y_nominal_tot] > 0.0 ? (-GB) / s[S_Y_nominal_tot] : 0.0;
         }
         if (last >= 28) {
-            double Un = s[S_Un], ut = c.par[P_u_target];
-            if (Un < ut) s[S_wb] = s[S_wb] * (1.0 + c.par[P_wage_update_up] * (ut - Un));
-            else s[S_wb] = s[S_wb] * (1.0 - c.par[P_wage_update_down] * (Un - ut));
+            double Un = s[S_Un], ut = c.par()[P_u_target];
+            if (Un < ut) s[S_wb] = s[S_wb] * (1.0 + c.par()[P_wage_update_up] * (ut - Un));
+            else s[S_wb] = s[S_wb] * (1.0 - c.par()[P_wage_update_down] * (Un - ut));
         }
         if (last >= 29) s[S_timestep] = s[S_timestep] + 1.0;
     }
     share = __shfl_sync(FULL, share, 0);
     if (share > 0.0)
-        for (int h = L.W + c.lane; h < L.H; h += 32) c.PA[h] = c.PA[h] + share;
+        for (int h = L.W + c.lane; h < L.H; h += 32) c.PA()[h] = c.PA()[h] + share;
     __syncwarp();
 }
 
@@ -1055,16 +1076,20 @@ __device__ void run_period(Ctx &c)
 {
     const KArgs &a = *c.a;
     const int F = a.L.F, N = a.L.N, last = c.last;
+#ifdef CATS_PROFILE_PHASES
     long long t0 = 0;
     const bool prof = a.cycles && c.lane == 0 && blockIdx.x == 0;
     if (prof) t0 = clock64();
 #define TICK(slot) do { if (prof) { long long t1 = clock64(); a.cycles[slot] += t1 - t0; t0 = t1; } } while (0)
+#else
+#define TICK(slot) do { } while (0)
+#endif
     // phases 1-2: reset_gov_and_banking_variables!, set_bond_interest_rate! (cats.py:355-356)
     if (c.lane == 0) {
-        c.scal[S_gov_TA] = 0.0; c.scal[S_gov_G] = 0.0;
-        c.scal[S_bank_interest_income] = 0.0; c.scal[S_bank_bad_debt] = 0.0;
-        if (last >= 2) c.scal[S_gov_r_b] = c.par[P_interest_rate];
-        c.misc[M_STATUS] = 0;
+        c.scal()[S_gov_TA] = 0.0; c.scal()[S_gov_G] = 0.0;
+        c.scal()[S_bank_interest_income] = 0.0; c.scal()[S_bank_bad_debt] = 0.0;
+        if (last >= 2) c.scal()[S_gov_r_b] = c.par()[P_interest_rate];
+        c.misc()[M_STATUS] = 0;
     }
     __syncwarp();
     if (last < 3) return;
@@ -1117,12 +1142,7 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
     const Layout &L = a.L;
     Ctx c;
     c.sm = smem; c.a = &a;
-    c.scal = reinterpret_cast<double *>(smem + L.o_scal);
-    c.par = reinterpret_cast<double *>(smem + L.s_par);
-    c.Leff = reinterpret_cast<int *>(smem + L.o_Leff);
-    c.vac = reinterpret_cast<int *>(smem + L.s_vac);
-    c.misc = reinterpret_cast<int *>(smem + L.s_misc);
-    c.lane = threadIdx.x; c.lt = (1u << threadIdx.x) - 1u;
+    c.lane = threadIdx.x;
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 16);
     const long long b = blockIdx.x;
@@ -1130,9 +1150,6 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
     c.b = b;
     unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
     c.blob = blob;
-    c.Oc = reinterpret_cast<int *>(blob + L.o_Oc);
-    c.PA = reinterpret_cast<double *>(blob + L.o_PA);
-    c.perm = reinterpret_cast<double *>(blob + L.o_perm);
 
     // HBM -> smem: one TMA bulk copy of the resident prefix (aggregates, K-firm tables, head-counts)
     if (c.lane == 0) {
@@ -1143,8 +1160,8 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
     }
     // parameters (shared row or per-economy row) while the copy is in flight
     const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
-    for (int i = c.lane; i < N_PARAMS; i += 32) c.par[i] = pr[i];
-    if (c.lane == 0) c.par[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
+    for (int i = c.lane; i < N_PARAMS; i += 32) c.par()[i] = pr[i];
+    if (c.lane == 0) c.par()[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
     // zero the transients (debug images are deterministic; the queue masks must start clear)
     for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
     __syncwarp();
@@ -1153,16 +1170,16 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
 
     c.d.k0 = a.k0; c.d.k1 = a.k1;
     c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
-    c.d.t = a.T;
-    c.d.z_c = (int)c.par[P_z_c]; c.d.z_k = (int)c.par[P_z_k]; c.d.z_e = (int)c.par[P_z_e];
+    c.d.tp = &a.T;
+    c.d.tape_z = a.tape_z;
 
     for (int t = 0; t < a.n_periods; ++t) {
-        c.d.period = (uint32_t)c.scal[S_timestep];
+        c.d.period = (uint32_t)c.scal()[S_timestep];
         c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
         run_period<ZM>(c);
         __syncwarp();
         if (a.stats && c.lane < N_STATS) {
-            const double *s = c.scal;
+            const double *s = c.scal();
             double v;
             switch (c.lane) {
             case 0: v = s[S_Y_real]; break;       case 1: v = s[S_wb]; break;
@@ -1176,14 +1193,14 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
             }
             a.stats[((size_t)b * (size_t)a.n_periods + (size_t)t) * N_STATS + c.lane] = v;
         }
-        if (c.lane == 0 && c.misc[M_STATUS])
-            c.scal[S_status] = (double)((unsigned)c.scal[S_status] | (unsigned)c.misc[M_STATUS]);
+        if (c.lane == 0 && c.misc()[M_STATUS])
+            c.scal()[S_status] = (double)((unsigned)c.scal()[S_status] | (unsigned)c.misc()[M_STATUS]);
         __syncwarp();
     }
     // a26 _get_obs (cats.py:466-481 / 655-671), a21 terminated, status
     if (a.obs) {
         for (int i = c.lane; i < a.n_agents; i += 32) {
-            double yp = c.cf(C_Y_prev)[i], yd = c.cf(C_Yd)[i], p = c.cf(C_P)[i], ap = c.scal[S_price];
+            double yp = c.cf(C_Y_prev)[i], yd = c.cf(C_Yd)[i], p = c.cf(C_P)[i], ap = c.scal()[S_price];
             double o0, o1;
             if (a.flags & CATS_FLAG_LOG) {
                 o0 = det_log(yp + 1e-8) - det_log(yd + 1e-8);
@@ -1194,8 +1211,8 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         }
     }
     if (c.lane == 0) {
-        if (a.terminated) a.terminated[b] = c.scal[S_terminated] != 0.0 ? 1 : 0;
-        if (a.status) a.status[b] = (unsigned)c.scal[S_status];
+        if (a.terminated) a.terminated[b] = c.scal()[S_terminated] != 0.0 ? 1 : 0;
+        if (a.status) a.status[b] = (unsigned)c.scal()[S_status];
     }
     if (a.debug) {
         // transients image (cats_workset_field_info): Ld vac cFtot cKdem cYstock cvalinv kFtot kYstock
@@ -1208,8 +1225,8 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         for (int i = c.lane; i < nf; i += 32) {
             // Ld == Leff + vac; before the credit phase vac only carries Ld and reads as 0
             const bool isk = i >= L.F;
-            reinterpret_cast<int *>(img + L.d_Ld)[i] = c.last >= (isk ? 8 : 7) ? c.Leff[i] + c.vac[i] : 0;
-            reinterpret_cast<int *>(img + L.d_vac)[i] = c.last >= (isk ? 10 : 9) ? c.vac[i] : 0;
+            reinterpret_cast<int *>(img + L.d_Ld)[i] = c.last >= (isk ? 8 : 7) ? c.Leff()[i] + c.vac()[i] : 0;
+            reinterpret_cast<int *>(img + L.d_vac)[i] = c.last >= (isk ? 10 : 9) ? c.vac()[i] : 0;
         }
         for (int f = c.lane; f < L.F; f += 32) {
             reinterpret_cast<double *>(img + L.d_cFtot)[f] = c.at(L.s_cFtot)[f];
@@ -1279,7 +1296,7 @@ static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 constexpr int kThreads = 32;    // one warp per economy
 #ifndef CATS_MIN_BLOCKS
-#define CATS_MIN_BLOCKS 16
+#define CATS_MIN_BLOCKS 20
 #endif
 constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
 typedef void (*KernelFn)(const KArgs);
@@ -1396,6 +1413,14 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
     return CATS_OK;
 }
 
+// development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
+static int smem_pad()
+{
+    static int pad = -1;
+    if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
+    return pad;
+}
+
 static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, int *num_sms)
 {
     int dev = 0;
@@ -1403,11 +1428,12 @@ static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, in
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (L.smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem);
+    const int smem = L.smem + smem_pad();
+    if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1464,6 +1490,7 @@ int cats_step(const cats_step_args *s)
     KArgs a;
     a.L = make_layout(s->W, s->F, s->N);
     a.T = TapeOff{};
+    a.tape_z[0] = a.tape_z[1] = a.tape_z[2] = 0;
     a.blobs = (unsigned char *)s->d_blobs; a.B = s->B;
     a.params = s->d_params; a.params_stride = s->params_stride;
     a.k0 = (uint32_t)s->seed; a.k1 = (uint32_t)(s->seed >> 32);
@@ -1477,13 +1504,14 @@ int cats_step(const cats_step_args *s)
     a.cycles = g_cycles;
     if (s->d_tape) {
         a.T = make_tape(s->W, s->F, s->N, s->tape_z[0], s->tape_z[1], s->tape_z[2]);
+        a.tape_z[0] = s->tape_z[0]; a.tape_z[1] = s->tape_z[1]; a.tape_z[2] = s->tape_z[2];
     }
     int occ = 0, sms = 0;
     KernelFn fn = select_kernel(s->max_z);
     if (int rc = configure_kernel(a.L, fn, &occ, &sms)) return rc;
     // one block (= one warp) per economy: the hardware block scheduler balances economies of
     // different length over the SMs; `occ` of them are resident per SM
-    fn<<<(unsigned)s->B, kThreads, a.L.smem, (cudaStream_t)s->stream>>>(a);
+    fn<<<(unsigned)s->B, kThreads, a.L.smem + smem_pad(), (cudaStream_t)s->stream>>>(a);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));

@@ -106,7 +106,7 @@ inline Layout make_layout(int W, int F, int N)
     if (2ll * W > u) u = 2ll * W;
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;
-    L.s_misc = (int32_t)o; o += 64;
+    L.s_misc = (int32_t)o; o += 192;   // status | mbarrier | OrderKeys | goods-market constants
     L.smem = (int32_t)o;
     // debug image
     o = 0;

@@ -2,6 +2,7 @@
 import csv, re, subprocess, sys, collections
 rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+nep = float(sys.argv[5]) if len(sys.argv) > 5 else 0
 import tempfile, os
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
@@ -40,4 +41,5 @@ print(f"total warp-inst {ti}  samples {ts}")
 for key, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     text = ""
     if key and key[0] in src and key[1] - 1 < len(src[key[0]]): text = src[key[0]][key[1] - 1].strip()[:90]
-    print(f"{v[1] / ts * 100:5.1f}% smp {v[0] / ti * 100:5.1f}% inst  {key}: {text}")
+    if nep: print(f"{v[1] / ts * 100:5.1f}% smp {v[0] / nep:8.1f} inst/ep  {key}: {text}")
+    else: print(f"{v[1] / ts * 100:5.1f}% smp {v[0] / ti * 100:5.1f}% inst  {key}: {text}")

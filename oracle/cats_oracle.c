@@ -230,32 +230,51 @@ static void sample_distinct(const uint32_t *words, int n, int z, int32_t *out)
     }
 }
 
-/* keyed bijection on [0,n) (visiting order of a market): 4 rounds of
- * x = (x*(m|1) + a) mod 2^b ; x ^= x >> s, cycle-walked into [0,n).                          */
-typedef struct { uint32_t m[4], a[4], mask; int s; int n; } Perm;
+/* keyed bijection on [0,n) (visiting order of a market), docs/MODEL.md 3.3: an alternating
+ * 4-round Feistel network on [0,a) x [0,b), a = smallest integer with a*a >= n, b = ceil(n/a),
+ * x = L*b + R, cycle-walked into [0,n) (a*b - n < a: almost never).  Round keys: the 4 words of
+ * Philox block 0, phase ORDER, agent = market id. */
+typedef struct { uint32_t k[4], a, b, m; int n; } Perm;
+
+static void perm_dims(int n, uint32_t *pa, uint32_t *pb, uint32_t *pm)
+{
+    uint32_t a = 1;
+    while ((uint64_t)a * a < (uint64_t)n) ++a;
+    uint32_t b = ((uint32_t)n + a - 1) / a;
+    *pa = a; *pb = b;
+    *pm = b > 1 ? (uint32_t)(((uint64_t)1 << 32) / b) + 1u : 0u;   /* L = mulhi32(x, m) == x / b for x < 2^23 */
+}
+
+static uint32_t perm_hash(uint32_t v, uint32_t k)
+{
+    uint32_t x = v * 0x9E3779B1u + k;
+    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    return x;
+}
 
 static void perm_init(const Econ *e, int market, int n, Perm *p)
 {
-    uint32_t w0[4], w1[4];
-    econ_philox(e, (uint32_t)market, PH_ORDER, 0, w0);
-    econ_philox(e, (uint32_t)market, PH_ORDER, 1, w1);
-    int b = 1;
-    while ((1u << b) < (uint32_t)n) ++b;
-    p->mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-    p->s = b / 2 > 0 ? b / 2 : 1;
+    uint32_t w[4];
+    econ_philox(e, (uint32_t)market, PH_ORDER, 0, w);
+    for (int r = 0; r < 4; ++r) p->k[r] = w[r];
     p->n = n;
-    p->m[0] = w0[0] | 1u; p->m[1] = w0[1] | 1u; p->m[2] = w1[0] | 1u; p->m[3] = w1[1] | 1u;
-    p->a[0] = w0[2]; p->a[1] = w0[3]; p->a[2] = w1[2]; p->a[3] = w1[3];
+    perm_dims(n, &p->a, &p->b, &p->m);
 }
 
 static int perm_at(const Perm *p, int pos)
 {
     uint32_t x = (uint32_t)pos;
+    const uint32_t a = p->a, b = p->b;
     do {
-        for (int r = 0; r < 4; ++r) {
-            x = (x * p->m[r] + p->a[r]) & p->mask;
-            x ^= x >> p->s;
-        }
+        uint32_t L = b > 1 ? (uint32_t)(((uint64_t)x * p->m) >> 32) : x;
+        uint32_t R = x - L * b;
+        L += (uint32_t)(((uint64_t)perm_hash(R, p->k[0]) * a) >> 32); if (L >= a) L -= a;
+        R += (uint32_t)(((uint64_t)perm_hash(L, p->k[1]) * b) >> 32); if (R >= b) R -= b;
+        L += (uint32_t)(((uint64_t)perm_hash(R, p->k[2]) * a) >> 32); if (L >= a) L -= a;
+        R += (uint32_t)(((uint64_t)perm_hash(L, p->k[3]) * b) >> 32); if (R >= b) R -= b;
+        x = L * b + R;
     } while (x >= (uint32_t)p->n);
     return (int)x;
 }

@@ -195,31 +195,45 @@ struct Draws {
     }
 };
 
-// visiting order of a market: tape permutation, or the keyed bijection of docs/MODEL.md 3.3.
+// visiting order of a market: tape permutation, or the keyed bijection of docs/MODEL.md 3.3 (an
+// alternating 4-round Feistel network on [0,a) x [0,b), a*b >= n, cycle-walked into [0,n)).
 // The round keys live in shared memory (OrderKeys) and are re-read at every use: they are needed
 // once per 32 agents, and registers are what bounds how many economies are resident per SM.
+struct OrderDims { uint32_t a, b, m, n; };   // computed on the host: they depend on the market size only
 struct OrderKeys {
-    uint32_t m[4], a[4], mask, s, n, pad;
+    uint32_t k[4], a, b, m, n;
     const int *tape_order;
 };
+inline OrderDims make_order_dims(int n)
+{
+    OrderDims d; uint32_t a = 1;
+    while ((uint64_t)a * a < (uint64_t)n) ++a;
+    d.a = a; d.b = ((uint32_t)n + a - 1) / a; d.n = (uint32_t)n;
+    d.m = d.b > 1 ? (uint32_t)(((uint64_t)1 << 32) / d.b) + 1u : 0u;   // mulhi32(x, m) == x / b for x < 2^23
+    return d;
+}
+__device__ __forceinline__ uint32_t perm_hash(uint32_t v, uint32_t k)
+{
+    uint32_t x = v * 0x9E3779B1u + k;
+    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    return x;
+}
 struct Order {
     volatile OrderKeys *k;
-    __device__ __forceinline__ void init(const Draws &d, int market, int n, OrderKeys *keys, int lane)
+    __device__ __forceinline__ void init(const Draws &d, int market, const OrderDims &dims, OrderKeys *keys, int lane)
     {
         k = keys;
         if (lane == 0) {
-            keys->n = (uint32_t)n; keys->tape_order = nullptr;
+            keys->a = dims.a; keys->b = dims.b; keys->m = dims.m; keys->n = dims.n;
+            keys->tape_order = nullptr;
             if (d.tape) {
                 uint32_t off = market == MKT_JOB ? d.tp->job_order : market == MKT_CAP ? d.tp->cap_order : d.tp->goods_order;
                 keys->tape_order = reinterpret_cast<const int *>(d.tape + off);
             } else {
-                uint4 w0 = d.philox((uint32_t)market, PH_ORDER, 0), w1 = d.philox((uint32_t)market, PH_ORDER, 1);
-                int b = 1;
-                while ((1u << b) < (uint32_t)n) ++b;
-                keys->mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-                keys->s = (uint32_t)(b / 2 > 0 ? b / 2 : 1);
-                keys->m[0] = w0.x | 1u; keys->m[1] = w0.y | 1u; keys->m[2] = w1.x | 1u; keys->m[3] = w1.y | 1u;
-                keys->a[0] = w0.z; keys->a[1] = w0.w; keys->a[2] = w1.z; keys->a[3] = w1.w;
+                const uint4 w = d.philox((uint32_t)market, PH_ORDER, 0);
+                keys->k[0] = w.x; keys->k[1] = w.y; keys->k[2] = w.z; keys->k[3] = w.w;
             }
         }
         __syncwarp();
@@ -228,15 +242,17 @@ struct Order {
     {
         const int *to = k->tape_order;
         if (to) return to[pos];
-        const uint32_t m0 = k->m[0], m1 = k->m[1], m2 = k->m[2], m3 = k->m[3];
-        const uint32_t a0 = k->a[0], a1 = k->a[1], a2 = k->a[2], a3 = k->a[3];
-        const uint32_t mask = k->mask, s = k->s, n = k->n;
+        const uint32_t a = k->a, b = k->b, m = k->m, n = k->n;
+        const uint32_t k0 = k->k[0], k1 = k->k[1], k2 = k->k[2], k3 = k->k[3];
         uint32_t x = (uint32_t)pos;
         do {
-            x = (x * m0 + a0) & mask; x ^= x >> s;
-            x = (x * m1 + a1) & mask; x ^= x >> s;
-            x = (x * m2 + a2) & mask; x ^= x >> s;
-            x = (x * m3 + a3) & mask; x ^= x >> s;
+            uint32_t L = b > 1 ? __umulhi(x, m) : x;
+            uint32_t R = x - L * b;
+            L += __umulhi(perm_hash(R, k0), a); if (L >= a) L -= a;
+            R += __umulhi(perm_hash(L, k1), b); if (R >= b) R -= b;
+            L += __umulhi(perm_hash(R, k2), a); if (L >= a) L -= a;
+            R += __umulhi(perm_hash(L, k3), b); if (R >= b) R -= b;
+            x = L * b + R;
         } while (x >= n);
         return (int)x;
     }
@@ -291,6 +307,19 @@ __device__ __forceinline__ void fx_add(unsigned long long *acc, unsigned long lo
     const unsigned old = atomicAdd(&w[0], lo);
     hi += (old + lo < old) ? 1u : 0u;
     if (hi) atomicAdd(&w[1], hi);
+}
+
+// a / b, bit-identical to the IEEE quotient.  The compiler's fp64 division drops into a ~60
+// instruction subroutine for the WHOLE warp as soon as one lane has a zero (or denormal) dividend --
+// and zero dividends are common here (idle lanes, households without wealth, firms without a
+// dividend).  +-0 / (positive finite) is +-0, so those lanes divide 1.0 instead and keep their zero.
+__device__ __forceinline__ double div_nz(double a, double b)
+{
+    const bool z = (a == 0.0) && (b > 0.0) && (b < __longlong_as_double(0x7ff0000000000000LL));
+    double num = z ? 1.0 : a;
+    asm volatile("" : "+d"(num));   // keep the compiler from folding this back into a / b
+    const double q = num / b;
+    return z ? a : q;
 }
 
 __device__ __forceinline__ int d2count(double x)

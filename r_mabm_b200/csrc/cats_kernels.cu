@@ -35,6 +35,7 @@ namespace cats {
 struct KArgs {
     Layout L;
     TapeOff T;
+    OrderDims od[3];   // visiting-order network dimensions of the job, capital and goods markets
     unsigned char *blobs;
     long long B;
     const double *params;
@@ -381,7 +382,7 @@ __device__ void phase_job_search(Ctx &c)
     const Layout &L = c.a->L;
     const int W = L.W, nf = L.F + L.N, lane = c.lane;
     const int z = c.z_e() < nf ? c.z_e() : nf;
-    Order ord; ord.init(c.d, MKT_JOB, W, c.okeys(), lane);
+    Order ord; ord.init(c.d, MKT_JOB, c.a->od[MKT_JOB], c.okeys(), lane);
     unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
     int total = 0;
     for (int base = 0; base < W; base += 128) {
@@ -497,7 +498,7 @@ __device__ void phase_capital_market(Ctx &c)
     const Layout &L = c.a->L;
     const int F = L.F, N = L.N, lane = c.lane;
     const int z = c.z_k() < N ? c.z_k() : N;
-    Order ord; ord.init(c.d, MKT_CAP, F, c.okeys(), lane);
+    Order ord; ord.init(c.d, MKT_CAP, c.a->od[MKT_CAP], c.okeys(), lane);
     double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.s_kYstock);
     double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
     double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
@@ -639,7 +640,7 @@ __device__ void phase_goods_market(Ctx &c)
     const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
     MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
-    Order ord; ord.init(c.d, MKT_GOODS, H, c.okeys(), lane);
+    Order ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
     // market constants: computed once, parked in shared memory and re-read per chunk (registers)
     enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
@@ -680,9 +681,9 @@ __device__ void phase_goods_market(Ctx &c)
             const double price = gk[G_price];
             double ir;
             if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
-            else ir = dinc / price;
+            else ir = div_nz(dinc, price);
             pm = pm * gk[G_xi] + gk[G_omxi] * ir;
-            const double target = pm + (gk[G_chi] * pa) / price;
+            const double target = pm + div_nz(gk[G_chi] * pa, price);
             b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
@@ -724,7 +725,12 @@ __device__ void phase_goods_market(Ctx &c)
                     }
                 }
             }
-            if (moved) d_t = b / p_t;
+            {   // idle lanes divide 1 / 1: a zero dividend would drag the whole warp into the division slow path
+                double num = moved ? b : 1.0, den = moved ? p_t : 1.0;
+                asm volatile("" : "+d"(num), "+d"(den));
+                const double q = num / den;
+                if (moved) d_t = q;
+            }
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
             const bool mine = (pend >> lane) & 1u;
             const bool has = mine && term >= 0;
@@ -1490,6 +1496,8 @@ int cats_step(const cats_step_args *s)
     KArgs a;
     a.L = make_layout(s->W, s->F, s->N);
     a.T = TapeOff{};
+    a.od[MKT_JOB] = make_order_dims(s->W); a.od[MKT_CAP] = make_order_dims(s->F);
+    a.od[MKT_GOODS] = make_order_dims(s->W + s->F + s->N);
     a.tape_z[0] = a.tape_z[1] = a.tape_z[2] = 0;
     a.blobs = (unsigned char *)s->d_blobs; a.B = s->B;
     a.params = s->d_params; a.params_stride = s->params_stride;

@@ -280,14 +280,10 @@ __device__ void phase_fire(Ctx &c, int limit)
     const Layout &L = c.a->L;
     const int W = L.W, lane = c.lane;
     int *ic = c.iat(L.s_ic);    // per firm: pooled head-count (low 16 bits) | pool cursor (high 16 bits)
+    // pooled head-count of an over-staffed firm == its Leff (#{w : Oc[w] == f} == Leff[f] is an invariant)
     bool over = false;
-    for (int f = lane; f < limit; f += 32) { over |= c.vac()[f] < 0; ic[f] = 0; }
+    for (int f = lane; f < limit; f += 32) { const bool o = c.vac()[f] < 0; over |= o; ic[f] = o ? c.Leff()[f] : 0; }
     if (!__any_sync(FULL, over)) return;
-    __syncwarp();
-    for (int w = lane; w < W; w += 32) {
-        int f = c.Oc()[w];
-        if (f >= 0 && f < limit && c.vac()[f] < 0) atomicAdd(&ic[f], 1);
-    }
     __syncwarp();
     const int cap = L.U_bytes / 8;
     int *pool_w = c.iat(L.s_U);
@@ -342,8 +338,11 @@ __device__ void phase_fire(Ctx &c, int limit)
         }
         const int total = base;
         if (total > 0) {
+            int fnext = lane < W ? c.Oc()[lane] : -1;
+#pragma unroll 1
             for (int w = lane; w < W; w += 32) {
-                int f = c.Oc()[w];
+                const int f = fnext;
+                fnext = w + 32 < W ? c.Oc()[w + 32] : -1;   // next load in flight while this worker is handled
                 if (f >= f0 && f < f1 && c.vac()[f] < 0) {
                     int slot = atomicAdd(&ic[f], 0x10000) >> 16;
                     pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
@@ -1028,7 +1027,13 @@ __device__ void phase_bankrupt(Ctx &c)
             c.kf(K_div_income)[i] = 0.0;
             c.Leff()[F + i] = 0;
         }
-        for (int w = c.lane; w < W; w += 32) { int o = c.Oc()[w]; if (o >= 0 && bad[o]) c.Oc()[w] = -1; }
+        for (int w0 = c.lane; w0 < W; w0 += 32 * 4) {
+            int oo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int w = w0 + 32 * u; oo[u] = w < W ? c.Oc()[w] : -1; }   // 4 loads in flight
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (oo[u] >= 0 && bad[oo[u]]) c.Oc()[w0 + 32 * u] = -1;
+        }
     }
     __syncwarp();
     {

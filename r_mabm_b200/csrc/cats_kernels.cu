@@ -1307,7 +1307,7 @@ static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 constexpr int kThreads = 32;    // one warp per economy
 #ifndef CATS_MIN_BLOCKS
-#define CATS_MIN_BLOCKS 20
+#define CATS_MIN_BLOCKS 18
 #endif
 constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
 typedef void (*KernelFn)(const KArgs);

@@ -286,6 +286,21 @@ __device__ __forceinline__ void sort_by_price(int (&cand)[ZM], double (&pr)[ZM],
     }
 }
 
+// ascending sort of ZM packed 32-bit keys, register only (min / max sorting network)
+template <int ZM>
+__device__ __forceinline__ void sort_keys(unsigned (&key)[ZM])
+{
+    auto cx = [&](int i, int j) { const unsigned a = key[i], b = key[j]; key[i] = min(a, b); key[j] = max(a, b); };
+    if (ZM == 2) { cx(0, 1); }
+    else if (ZM == 5) {
+        cx(0, 1); cx(3, 4); cx(2, 4); cx(2, 3); cx(1, 4); cx(0, 3); cx(0, 2); cx(1, 3); cx(1, 2);
+    } else {
+        static_assert(ZM == 2 || ZM == 5 || ZM == 8, "sorting networks exist for 2, 5 and 8 slots");
+        cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7); cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7); cx(1, 2); cx(5, 6);
+        cx(0, 4); cx(1, 5); cx(2, 6); cx(3, 7); cx(2, 4); cx(3, 5); cx(1, 2); cx(3, 4); cx(5, 6);
+    }
+}
+
 // demand registered at a consumption-goods seller: 2^-40 fixed point, wrap-around add (MODEL.md 4.4)
 __device__ __forceinline__ unsigned long long fx_from(double x)
 {
@@ -307,6 +322,12 @@ __device__ __forceinline__ void fx_add(unsigned long long *acc, unsigned long lo
     const unsigned old = atomicAdd(&w[0], lo);
     hi += (old + lo < old) ? 1u : 0u;
     if (hi) atomicAdd(&w[1], hi);
+}
+
+// the same add on an accumulator in global memory: one fire-and-forget 64-bit reduction at L2
+__device__ __forceinline__ void fx_red(unsigned long long *acc, unsigned long long x)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(acc), "l"(x) : "memory");
 }
 
 // a / b, bit-identical to the IEEE quotient.  The compiler's fp64 division drops into a ~60

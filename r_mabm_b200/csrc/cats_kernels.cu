@@ -434,10 +434,14 @@ __device__ void phase_job_search(Ctx &c)
     }
 }
 
-// One consumption-goods seller as the market sees it.  The SoA rows (P, Yd, Q, stock) are packed
-// into this 32-byte record when production is decided and unpacked when the market closes.
-// acc: demand expressed at the seller, 2^-40 fixed point (order-independent: MODEL.md 4.4).
-struct __align__(16) MktRec { double ys, p, q; unsigned long long acc; };
+// One consumption-goods seller as the market sees it.  The SoA rows (P, Q, stock) are packed into
+// this 32-byte record when production is decided and unpacked when the market closes.
+// cls: price class = number of strictly cheaper sellers.  Sorting a household's candidates by
+// (cls, draw index) IS the stable sort by price of MODEL.md 5.20, done on small integers.
+// The demand expressed at a seller (2^-40 fixed point, order-independent: MODEL.md 4.4) is
+// accumulated in the seller's Yd slot of the blob with fire-and-forget 64-bit reductions (RED at
+// L2): nobody reads it before the market closes, so no lane ever waits for it.
+struct __align__(16) MktRec { double ys, p, q; unsigned cls, spare; };
 
 // a11 firms_produce! (cats.py:384-385)
 __device__ void phase_produce(Ctx &c)
@@ -462,9 +466,23 @@ __device__ void phase_produce(Ctx &c)
         if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
         double P = c.cf(C_P)[f];
         if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
-        MktRec r; r.ys = Y; r.p = P; r.q = 0.0; r.acc = 0ull; mkt[f] = r;
+        MktRec r; r.ys = Y; r.p = P; r.q = 0.0; r.cls = 0u; r.spare = 0u; mkt[f] = r;
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
-        if (last < 20) { c.cf(C_Q)[f] = 0.0; c.cf(C_Yd)[f] = 0.0; }   // else written when the goods market closes
+        c.cf(C_Yd)[f] = 0.0;                     // == the all-zero demand accumulator of the goods market
+        if (last < 20) c.cf(C_Q)[f] = 0.0;       // else written when the goods market closes
+    }
+    if (last >= 20) {
+        // price classes of the sellers (prices are final for the period from here on)
+        __syncwarp();
+        for (int f0 = c.lane; f0 < F; f0 += 64) {
+            const int f1 = f0 + 32;
+            const double pa = mkt[f0].p, pb = f1 < F ? mkt[f1].p : 0.0;
+            unsigned na = 0u, nb = 0u;
+#pragma unroll 4
+            for (int g = 0; g < F; ++g) { const double pg = mkt[g].p; na += pg < pa ? 1u : 0u; nb += pg < pb ? 1u : 0u; }
+            mkt[f0].cls = na;
+            if (f1 < F) mkt[f1].cls = nb;
+        }
     }
     if (last >= 15) {
         for (int i = c.lane; i < N; i += 32) {
@@ -639,6 +657,7 @@ __device__ void phase_goods_market(Ctx &c)
     const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
     MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
     Order ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
     // market constants: computed once, parked in shared memory and re-read per chunk (registers)
     enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
@@ -693,15 +712,17 @@ __device__ void phase_goods_market(Ctx &c)
         unsigned long long cp0 = 0ull, cp1 = 0ull;
         unsigned pend = __ballot_sync(FULL, b > 0.0);
         if (b > 0.0) {
-            int cand[ZM]; double pr[ZM];
+            int cand[ZM]; unsigned key[ZM];
             c.d.candidates<ZM>(PH_GOODS, h, F, z, cand);
+            // key = price class (14 bits) | draw index (3 bits) | seller (14 bits): F <= 16383
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) pr[k] = k < z ? mkt[cand[k]].p : INF;
-            sort_by_price<ZM>(cand, pr, z);
+            for (int k = 0; k < ZM; ++k)
+                key[k] = k < z ? (mkt[cand[k]].cls << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
+            sort_keys<ZM>(key);
 #pragma unroll
             for (int k = 0; k < ZM; ++k) {
-                if (k < 4) cp0 |= (unsigned long long)(unsigned)cand[k] << (16 * k);
-                else cp1 |= (unsigned long long)(unsigned)cand[k] << (16 * (k - 4));
+                if (k < 4) cp0 |= (unsigned long long)(key[k] & 0x3fffu) << (16 * k);
+                else cp1 |= (unsigned long long)(key[k] & 0x3fffu) << (16 * (k - 4));
             }
         }
         int nrem = b > 0.0 ? z : 0, term = -1;
@@ -719,7 +740,7 @@ __device__ void phase_goods_market(Ctx &c)
                         cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
                         MktRec *r = &mkt[cnd];
                         const double2 yp = *reinterpret_cast<const double2 *>(r);   // stock, price
-                        fx_add(&r->acc, xb);
+                        fx_red(&acc[cnd], xb);
                         if (yp.x > 0.0) { term = cnd; p_t = yp.y; dirty = false; moved = true; }
                     }
                 }
@@ -776,10 +797,17 @@ __device__ void phase_goods_market(Ctx &c)
         }
         if (h >= 0) c.PA()[h] = pa + b;   // involuntary saving
     }
-    // close: unpack the seller records
+    // close: unpack the seller records.  The reductions above were issued by other lanes: fence, then
+    // read the accumulators where they live (L2)
+    __threadfence();
+    __syncwarp();
     {
         double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
-        for (int f = lane; f < F; f += 32) { const MktRec r = mkt[f]; Yd[f] = (fx_to(r.acc) * gk[G_price]) / r.p; Q[f] = r.q; }
+        for (int f = lane; f < F; f += 32) {
+            const MktRec r = mkt[f];
+            const unsigned long long a = __ldcg(&acc[f]);
+            Yd[f] = (fx_to(a) * gk[G_price]) / r.p; Q[f] = r.q;
+        }
     }
     __syncwarp();
 }
@@ -1307,7 +1335,7 @@ static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 constexpr int kThreads = 32;    // one warp per economy
 #ifndef CATS_MIN_BLOCKS
-#define CATS_MIN_BLOCKS 18
+#define CATS_MIN_BLOCKS 24
 #endif
 constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
 typedef void (*KernelFn)(const KArgs);
@@ -1326,7 +1354,8 @@ static int fail(int code, const char *fmt, const char *detail)
 static int check_sizes(int W, int F, int N)
 {
     if (W < 1 || F < 1 || N < 1) return fail(CATS_EINVAL, "W, F, N must be >= 1%s", "");
-    if (W > 65535 || F + N > 32767) return fail(CATS_EINVAL, "economy too large for this build (W <= 65535, F + N <= 32767)%s", "");
+    if (W > 65535 || F + N > 32767 || F > 16383)
+        return fail(CATS_EINVAL, "economy too large for this build (W <= 65535, F <= 16383, F + N <= 32767)%s", "");
     return CATS_OK;
 }
 
@@ -1443,6 +1472,10 @@ static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, in
     if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    // the whole unified L1 as shared memory: residency (economies per SM) is what hides latency here,
+    // and the streamed tail goes through L2 anyway
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "occupancy query: %s", cudaGetErrorString(e));

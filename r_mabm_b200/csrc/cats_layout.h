@@ -33,7 +33,7 @@ enum {
     P_interest_rate, P_subsidy, P_maastricht, P_target_deficit, P_tax_rate, P_wage_update_up,
     P_wage_update_down, P_u_target, P_wb, P_tax_rate_d, P_r_f, P_E_threshold_scale,
     // derived, filled on chip
-    P_log1mtheta = 34, P_SLOTS = 40
+    P_log1mtheta = 34, P_SLOTS = 36
 };
 
 // scalar slots of the blob (model.agg / bank / gov of the reference, cats.py:567-607)
@@ -106,7 +106,7 @@ inline Layout make_layout(int W, int F, int N)
     if (2ll * W > u) u = 2ll * W;
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;
-    L.s_misc = (int32_t)o; o += 192;   // status | mbarrier | OrderKeys | goods-market constants
+    L.s_misc = (int32_t)o; o += 176;   // status | mbarrier | OrderKeys | goods-market constants (9 x f64)
     L.smem = (int32_t)o;
     // debug image
     o = 0;

@@ -776,15 +776,16 @@ void ph_get_paid(Econ *e)
 void ph_cons_budget(Econ *e)
 {
     const double xi = e->par[P_xi], chi = e->par[P_chi], price = e->scal[S_price];
+    const double rpavg = 1.0 / price; /* real values are nominal * (1 / price): MODEL.md 4.5 */
     for (int h = 0; h < e->H; ++h) {
         double inc = h < e->W ? e->income[h]
                    : h < e->W + e->F ? e->c[C_div_income][h - e->W]
                                      : e->k[K_div_income][h - e->W - e->F];
-        double ir = inc / price;
+        double ir = inc * rpavg;
         double pm = e->perm[h] * xi + (1.0 - xi) * ir;
         e->perm[h] = pm;
         double pa = e->PA[h];
-        double target = pm + (chi * pa) / price;
+        double target = pm + (chi * pa) * rpavg;
         double b = target * price;
         if (b > pa) b = pa;
         if (!(b > 0.0)) b = 0.0;
@@ -815,6 +816,8 @@ void ph_goods_market(Econ *e)
     const double *P = e->c[C_P];
     const double pavg = e->scal[S_price], rpavg = 1.0 / pavg;
     uint64_t *acc = (uint64_t *)xcalloc((size_t)e->F, 8);
+    double *rp = (double *)xcalloc((size_t)e->F, 8); /* 1 / P, once per seller (MODEL.md 4.5) */
+    for (int f = 0; f < e->F; ++f) rp[f] = 1.0 / P[f];
     for (int pos = 0; pos < e->H; ++pos) {
         int h = order_at(&o, pos);
         double b = e->budget[h];
@@ -829,14 +832,12 @@ void ph_goods_market(Econ *e)
             acc[best] += fx_from(b * rpavg);
             double ys = e->c_Ystock[best];
             if (ys > 0.0) {
-                double d = b / p;
+                double d = b * rp[best];
                 if (ys > d) {
                     e->c_Ystock[best] = ys - d;
-                    e->c[C_Q][best] = e->c[C_Q][best] + d;
                     b = 0.0;
                 } else {
                     b = b - ys * p;
-                    e->c[C_Q][best] = e->c[C_Q][best] + ys;
                     e->c_Ystock[best] = 0.0;
                 }
             }
@@ -844,8 +845,11 @@ void ph_goods_market(Econ *e)
         e->PA[h] = e->PA[h] + b; /* involuntary saving */
         e->budget[h] = b;
     }
-    for (int f = 0; f < e->F; ++f) e->c[C_Yd][f] = (fx_to(acc[f]) * pavg) / P[f];
-    free(acc);
+    for (int f = 0; f < e->F; ++f) {
+        e->c[C_Yd][f] = (fx_to(acc[f]) * pavg) * rp[f];
+        e->c[C_Q][f] = e->c[C_Y_prev][f] - e->c_Ystock[f]; /* sold = produced - left over */
+    }
+    free(acc); free(rp);
 }
 
 /* a17 firms_accounting! (cats.py:397-398) */

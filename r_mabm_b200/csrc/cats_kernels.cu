@@ -441,7 +441,9 @@ __device__ void phase_job_search(Ctx &c)
 // The demand expressed at a seller (2^-40 fixed point, order-independent: MODEL.md 4.4) is
 // accumulated in the seller's Yd slot of the blob with fire-and-forget 64-bit reductions (RED at
 // L2): nobody reads it before the market closes, so no lane ever waits for it.
-struct __align__(16) MktRec { double ys, p, q; unsigned cls, spare; };
+// rp = 1 / p: a purchase is b * rp (MODEL.md 4.5).  Sales are what is missing from the stock when
+// the market closes (Q = Y - stock), so the record carries no running total.
+struct __align__(16) MktRec { double ys, rp, p; unsigned cls, spare; };
 
 // a11 firms_produce! (cats.py:384-385)
 __device__ void phase_produce(Ctx &c)
@@ -466,7 +468,7 @@ __device__ void phase_produce(Ctx &c)
         if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
         double P = c.cf(C_P)[f];
         if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
-        MktRec r; r.ys = Y; r.p = P; r.q = 0.0; r.cls = 0u; r.spare = 0u; mkt[f] = r;
+        MktRec r; r.ys = Y; r.rp = 1.0 / P; r.p = P; r.cls = 0u; r.spare = 0u; mkt[f] = r;
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
         c.cf(C_Yd)[f] = 0.0;                     // == the all-zero demand accumulator of the goods market
         if (last < 20) c.cf(C_Q)[f] = 0.0;       // else written when the goods market closes
@@ -625,9 +627,10 @@ __device__ void phase_households_only(Ctx &c)
         if (h < L.W) { inc = c.Oc()[h] >= 0 ? wb * (1.0 - c.par()[P_tax_rate]) : sub; pa = pa + inc; }
         else inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
         if (c.last >= 19) {
-            double ir = inc / price;
+            const double rpavg = 1.0 / price;
+            double ir = inc * rpavg;
             pm = pm * xi + (1.0 - xi) * ir;
-            double target = pm + (chi * pa) / price;
+            double target = pm + (chi * pa) * rpavg;
             double b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
@@ -666,8 +669,9 @@ __device__ void phase_goods_market(Ctx &c)
         const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
         const double xi = c.par()[P_xi];
         const double net = wb * (1.0 - c.par()[P_tax_rate]);
-        gk[G_net] = net; gk[G_sub] = sub; gk[G_ir_emp] = net / price; gk[G_ir_un] = sub / price;
-        gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = 1.0 / price;
+        const double rp = 1.0 / price;
+        gk[G_net] = net; gk[G_sub] = sub; gk[G_ir_emp] = net * rp; gk[G_ir_un] = sub * rp;
+        gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = rp;
     }
     __syncwarp();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -699,9 +703,9 @@ __device__ void phase_goods_market(Ctx &c)
             const double price = gk[G_price];
             double ir;
             if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
-            else ir = div_nz(dinc, price);
+            else ir = dinc * rpavg;
             pm = pm * gk[G_xi] + gk[G_omxi] * ir;
-            const double target = pm + div_nz(gk[G_chi] * pa, price);
+            const double target = pm + (gk[G_chi] * pa) * rpavg;
             b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
@@ -726,12 +730,11 @@ __device__ void phase_goods_market(Ctx &c)
             }
         }
         int nrem = b > 0.0 ? z : 0, term = -1;
-        double p_t = 1.0, d_t = 0.0;
+        double d_t = 0.0;
         bool dirty = b > 0.0;
         unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
         while (pend) {
             // ---- walk: dirty lanes register demand seller by seller until one has stock
-            bool moved = false;
             while (__any_sync(FULL, dirty)) {
                 if (dirty) {
                     if (nrem == 0) { term = -1; dirty = false; }   // every candidate is sold out
@@ -739,31 +742,25 @@ __device__ void phase_goods_market(Ctx &c)
                         const int cnd = (int)(cp0 & 0xffffull);
                         cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
                         MktRec *r = &mkt[cnd];
-                        const double2 yp = *reinterpret_cast<const double2 *>(r);   // stock, price
+                        const double2 yr = *reinterpret_cast<const double2 *>(r);   // stock, 1 / price
                         fx_red(&acc[cnd], xb);
-                        if (yp.x > 0.0) { term = cnd; p_t = yp.y; dirty = false; moved = true; }
+                        if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; dirty = false; }
                     }
                 }
-            }
-            {   // idle lanes divide 1 / 1: a zero dividend would drag the whole warp into the division slow path
-                double num = moved ? b : 1.0, den = moved ? p_t : 1.0;
-                asm volatile("" : "+d"(num), "+d"(den));
-                const double q = num / den;
-                if (moved) d_t = q;
             }
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
             const bool mine = (pend >> lane) & 1u;
             const bool has = mine && term >= 0;
             const unsigned peers = __match_any_sync(FULL, has ? term : -1 - lane);
             unsigned rem = has ? (peers & lt) : 0u;
-            double ys = 0.0, q = 0.0;
-            if (has) { ys = mkt[term].ys; q = mkt[term].q; }
+            double ys = 0.0;
+            if (has) ys = mkt[term].ys;
             bool sold = false;
             while (__any_sync(FULL, rem != 0u)) {
                 const int src = rem ? __ffs(rem) - 1 : 0;
                 const double di = __shfl_sync(FULL, d_t, src);
                 if (rem) {
-                    if (!sold) { if (ys > di) { ys = ys - di; q = q + di; } else sold = true; }
+                    if (!sold) { if (ys > di) ys = ys - di; else sold = true; }
                     rem &= rem - 1;
                 }
             }
@@ -779,15 +776,15 @@ __device__ void phase_goods_market(Ctx &c)
                 else {
                     const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
                     MktRec *r = &mkt[term];
-                    if (full) { ys = ys - d_t; q = q + d_t; b = 0.0; done = true; }
+                    if (full) { ys = ys - d_t; b = 0.0; done = true; }
                     else {                                 // lane s: partial fill, then walk on
-                        b = b - ys * p_t; q = q + ys; ys = 0.0;
+                        b = b - ys * r->p; ys = 0.0;
                         term = -1;
                         dirty = b > 0.0;
                         done = !dirty;
                         xb = fx_from(b * rpavg);
                     }
-                    if (lastp) { r->ys = ys; r->q = q; }
+                    if (lastp) r->ys = ys;
                 }
             } else if (mine && so && has && term == xs) {
                 term = -1; dirty = true;                   // queued behind lane s at the exhausted seller
@@ -806,7 +803,7 @@ __device__ void phase_goods_market(Ctx &c)
         for (int f = lane; f < F; f += 32) {
             const MktRec r = mkt[f];
             const unsigned long long a = __ldcg(&acc[f]);
-            Yd[f] = (fx_to(a) * gk[G_price]) / r.p; Q[f] = r.q;
+            Yd[f] = (fx_to(a) * gk[G_price]) * r.rp; Q[f] = c.cf(C_Y_prev)[f] - r.ys;
         }
     }
     __syncwarp();
@@ -831,7 +828,7 @@ __device__ void phase_accounting(Ctx &c)
         double cv = c.cf(C_capital_value)[f];
         if (Kold != 0.0) dv = (dep * cv) / Kold;
         c.cf(C_capital_value)[f] = (cv - dv) + c.at(L.s_cvalinv)[f];
-        double RIC = mkt[f].p * mkt[f].q;
+        double RIC = mkt[f].p * c.cf(C_Q)[f];
         double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f];
         double deb = c.cf(C_deb)[f];
         double in = theta * deb;

@@ -404,6 +404,11 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// L2 prefetch of a contiguous region (16-byte granularity): one instruction, no destination, no wait
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

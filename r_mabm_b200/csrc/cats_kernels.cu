@@ -1136,6 +1136,7 @@ __device__ void run_period(Ctx &c)
     __syncwarp();
     TICK(1);
     if (last < 13) return;
+    if (c.lane == 0 && last >= 18) bulk_prefetch_l2(c.blob + a.L.o_PA, (uint32_t)(a.L.blob - a.L.o_PA));
     phase_job_search<ZM>(c);  // 13
     __syncwarp();
     TICK(2);
@@ -1193,6 +1194,9 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         fence_mbar_init();
         mbar_expect_tx(bar, (uint32_t)L.resident);
         bulk_g2s(smem, blob, (uint32_t)L.resident, bar);
+        // the streamed tail is first touched phases apart: pull what the firm phases and the labour
+        // market need (employment links, firm rows) into L2 now, household wealth before the goods market
+        bulk_prefetch_l2(blob + L.o_Oc, (uint32_t)(L.o_PA - L.o_Oc));
     }
     // parameters (shared row or per-economy row) while the copy is in flight
     const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);

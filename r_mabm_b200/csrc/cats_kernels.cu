@@ -157,8 +157,12 @@ __device__ void phase_firm_decisions(Ctx &c)
     double accC = 0.0, accK = 0.0;  // det_sum partials of new credit
     for (int f = c.lane; f < F; f += 32) {
         double *De = c.cf(C_De), *P = c.cf(C_P);
+        // every row value this firm needs, loaded before the first store (the rows share one base
+        // pointer: the compiler will not move a load over a store on its own)
         const double Yprev = c.cf(C_Y_prev)[f], Yd = c.cf(C_Yd)[f];
         double p = P[f], de = De[f];
+        const double K_f = c.cf(C_K)[f], barYK_f = c.cf(C_barYK)[f], liq_f = c.cf(C_liquidity)[f];
+        const double deb_f = c.cf(C_deb)[f], ir_f = c.cf(C_interest_r)[f], A_f = c.cf(C_A)[f];
         const double prevDe = de, prevP = p;
         // phase 3: a3 firms_decide_price_quantity! (cats.py:363)
         {
@@ -179,8 +183,8 @@ __device__ void phase_firm_decisions(Ctx &c)
             const double Iprob = c.par()[P_Iprob], barX = c.par()[P_barX], eta = c.par()[P_eta];
             double u = c.d.uniform(PH_INVEST, f);
             if (u < Iprob) {
-                double K = c.cf(C_K)[f];
-                double Kdes = c.cf(C_barYK)[f] / barX;
+                double K = K_f;
+                double Kdes = barYK_f / barX;
                 double depn = ((barX * K) * eta) / Iprob;
                 kd = (Kdes - K) + depn;
                 if (!(kd > 0.0)) kd = 0.0;
@@ -204,25 +208,25 @@ __device__ void phase_firm_decisions(Ctx &c)
                 if (de < alpha) de = alpha;
             }
         }
-        De[f] = de; P[f] = p;
         // phase 7: a7 firms_decide_labour! (cats.py:373)
         if (last >= 7) {
             double aa = ceil(de / alpha);
-            double bb = ceil((c.cf(C_K)[f] * c.par()[P_k]) / alpha);
+            double bb = ceil((K_f * c.par()[P_k]) / alpha);
             int Ld = d2count(aa < bb ? aa : bb);
             int vac = Ld - c.Leff()[f];
             // phase 9: a8 firms_get_credit! (cats.py:376)
             if (last >= 9) {
-                double liq = c.cf(C_liquidity)[f];
+                double liq = liq_f;
                 double need = (wb * (double)Ld + kd * c.scal()[S_price_k]) - liq;
-                double deb = c.cf(C_deb)[f], ir = c.cf(C_interest_r)[f], Ftot;
-                credit_one(c, need, c.par()[P_b1], c.par()[P_b2], deb, c.cf(C_A)[f], ir, Ftot, liq, Ld,
+                double deb = deb_f, ir = ir_f, Ftot;
+                credit_one(c, need, c.par()[P_b1], c.par()[P_b2], deb, A_f, ir, Ftot, liq, Ld,
                            c.Leff()[f], vac);
                 c.cf(C_deb)[f] = deb; c.cf(C_interest_r)[f] = ir; c.at(L.s_cFtot)[f] = Ftot;
                 accC = accC + Ftot;
             }
             c.vac()[f] = vac;
         }
+        De[f] = de; P[f] = p;
     }
     for (int i = c.lane; i < N; i += 32) {
         double *De = c.kf(K_De), *P = c.kf(K_P);
@@ -454,19 +458,19 @@ __device__ void phase_produce(Ctx &c)
     const double wb = c.scal()[S_wb], pk = c.scal()[S_price_k];
     MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
     for (int f = c.lane; f < F; f += 32) {
+        // loads first (see phase_firm_decisions)
+        const double K_f = c.cf(C_K)[f], De = c.cf(C_De)[f], deb = c.cf(C_deb)[f], ir_f = c.cf(C_interest_r)[f];
+        double P = c.cf(C_P)[f];
         double Leff = (double)c.Leff()[f];
-        double cap_l = Leff * alpha, cap_k = c.cf(C_K)[f] * k;
+        double cap_l = Leff * alpha, cap_k = K_f * k;
         double Yp = cap_l < cap_k ? cap_l : cap_k;
-        double De = c.cf(C_De)[f];
         double Y = De < Yp ? De : Yp;
         c.cf(C_Y_prev)[f] = Y;
-        double deb = c.cf(C_deb)[f];
-        double interests = c.cf(C_interest_r)[f] * deb;
+        double interests = ir_f * deb;
         double wages = wb * Leff;
         c.cf(C_interests)[f] = interests; c.cf(C_wages)[f] = wages;
         double Pl = 0.0;
         if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
-        double P = c.cf(C_P)[f];
         if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
         MktRec r; r.ys = Y; r.rp = 1.0 / P; r.p = P; r.cls = 0u; r.spare = 0u; mkt[f] = r;
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
@@ -819,30 +823,30 @@ __device__ void phase_accounting(Ctx &c)
     const MktRec *mkt = reinterpret_cast<const MktRec *>(c.sm + L.s_U);
     double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;   // det_sum partials
     for (int f = c.lane; f < F; f += 32) {
-        double Yp = c.cf(C_Y_prev)[f];
-        c.cf(C_barYK)[f] = delta * c.cf(C_barYK)[f] + (1.0 - delta) * (Yp / k);
+        // loads first (see phase_firm_decisions)
+        const double Yp = c.cf(C_Y_prev)[f], barYK = c.cf(C_barYK)[f], Kold = c.cf(C_K)[f];
+        const double inv_f = c.cf(C_investment)[f], cv = c.cf(C_capital_value)[f], Q_f = c.cf(C_Q)[f];
+        const double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f], deb = c.cf(C_deb)[f];
+        const double liq0 = c.cf(C_liquidity)[f], A0 = c.cf(C_A)[f], pa_owner = c.PA()[W + f];
+        c.cf(C_barYK)[f] = delta * barYK + (1.0 - delta) * (Yp / k);
         double dep = (eta * Yp) / k;
-        double Kold = c.cf(C_K)[f];
-        c.cf(C_K)[f] = (Kold - dep) + c.cf(C_investment)[f];
+        c.cf(C_K)[f] = (Kold - dep) + inv_f;
         double dv = 0.0;
-        double cv = c.cf(C_capital_value)[f];
         if (Kold != 0.0) dv = (dep * cv) / Kold;
         c.cf(C_capital_value)[f] = (cv - dv) + c.at(L.s_cvalinv)[f];
-        double RIC = mkt[f].p * c.cf(C_Q)[f];
-        double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f];
-        double deb = c.cf(C_deb)[f];
+        double RIC = mkt[f].p * Q_f;
         double in = theta * deb;
-        double liq = ((((c.cf(C_liquidity)[f] + RIC) + c.at(L.s_cFtot)[f]) - wages) - interests) - in;
+        double liq = ((((liq0 + RIC) + c.at(L.s_cFtot)[f]) - wages) - interests) - in;
         c.cf(C_deb)[f] = deb - in;
         double pi = ((RIC - wages) - interests) - dv;
-        double A = c.cf(C_A)[f] + pi;
+        double A = A0 + pi;
         double net = 0.0, dt = 0.0;
         if (pi > 0.0) {
             double dvd = divs * pi;
             liq = liq - dvd; A = A - dvd;
             net = dvd * (1.0 - taxd);
             dt = dvd - net;
-            c.PA()[W + f] = c.PA()[W + f] + net;
+            c.PA()[W + f] = pa_owner + net;
         }
         c.cf(C_div_income)[f] = net;
         c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;

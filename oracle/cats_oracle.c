@@ -249,8 +249,7 @@ static uint32_t perm_hash(uint32_t v, uint32_t k)
 {
     uint32_t x = v * 0x9E3779B1u + k;
     x ^= x >> 16;
-    x *= 0x85EBCA6Bu;
-    x ^= x >> 13;
+    x *= 0x85EBCA6Bu; /* only the high bits are used (mulhi by the half-domain size) */
     return x;
 }
 
@@ -701,6 +700,8 @@ void ph_capital_market(Econ *e)
     Order o; order_init(e, MKT_CAP, e->F, &o);
     int z = e->z_k < e->N ? e->z_k : e->N;
     double *Pk = e->k[K_P];
+    double *rp = (double *)xcalloc((size_t)e->N, 8); /* 1 / P, once per seller (MODEL.md 4.5) */
+    for (int i = 0; i < e->N; ++i) rp[i] = 1.0 / Pk[i];
     for (int pos = 0; pos < e->F; ++pos) {
         int f = order_at(&o, pos);
         double kd = e->c_Kdem[f];
@@ -713,17 +714,16 @@ void ph_capital_market(Econ *e)
             if (!(cb > 0.0 && kd > 0.0)) break;
             int best = cand[k];
             double pk = Pk[best];
-            double afford = cb / pk;
+            double afford = cb * rp[best];
             double want = afford < kd ? afford : kd;
             e->k[K_Yd][best] = e->k[K_Yd][best] + want;
             double ys = e->k_Ystock[best];
             if (ys > 0.0) {
                 double full = kd * pk;
                 double spend = cb < full ? cb : full;
-                double q = spend / pk;
+                double q = spend * rp[best];
                 if (ys > q) {
                     e->k_Ystock[best] = ys - q;
-                    e->k[K_Q][best] = e->k[K_Q][best] + q;
                     kd = kd - q; cb = cb - spend;
                     e->c[C_liquidity][f] = e->c[C_liquidity][f] - spend;
                     e->c[C_investment][f] = e->c[C_investment][f] + q;
@@ -732,7 +732,6 @@ void ph_capital_market(Econ *e)
                     double cost = ys * pk;
                     kd = kd - ys; cb = cb - cost;
                     e->c[C_liquidity][f] = e->c[C_liquidity][f] - cost;
-                    e->k[K_Q][best] = e->k[K_Q][best] + ys;
                     e->c[C_investment][f] = e->c[C_investment][f] + ys;
                     e->c_valinv[f] = e->c_valinv[f] + cost;
                     e->k_Ystock[best] = 0.0;
@@ -741,6 +740,7 @@ void ph_capital_market(Econ *e)
         }
         e->c_Kdem[f] = kd;
     }
+    free(rp);
 }
 
 /* a13 gov_adjusts_subsidy! (cats.py:389) */
@@ -898,6 +898,7 @@ void ph_accounting_k(Econ *e)
     int N = e->N;
     double *inst = (double *)xcalloc((size_t)N, 8), *dtax = (double *)xcalloc((size_t)N, 8);
     for (int i = 0; i < N; ++i) {
+        e->k[K_Q][i] = e->k[K_Yavail][i] - e->k_Ystock[i]; /* sold = available - left over */
         double RIC = e->k[K_P][i] * e->k[K_Q][i];
         e->k[K_inv][i] = (1.0 - e->par[P_inventory_depreciation]) * e->k_Ystock[i];
         double wages = e->k[K_wages][i], interests = e->k[K_interests][i];

@@ -216,8 +216,7 @@ __device__ __forceinline__ uint32_t perm_hash(uint32_t v, uint32_t k)
 {
     uint32_t x = v * 0x9E3779B1u + k;
     x ^= x >> 16;
-    x *= 0x85EBCA6Bu;
-    x ^= x >> 13;
+    x *= 0x85EBCA6Bu;   // only the high bits of x are used (mulhi by the half-domain size)
     return x;
 }
 struct Order {

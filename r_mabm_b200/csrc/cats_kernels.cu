@@ -480,14 +480,20 @@ __device__ void phase_produce(Ctx &c)
     if (last >= 20) {
         // price classes of the sellers (prices are final for the period from here on)
         __syncwarp();
-        for (int f0 = c.lane; f0 < F; f0 += 64) {
-            const int f1 = f0 + 32;
-            const double pa = mkt[f0].p, pb = f1 < F ? mkt[f1].p : 0.0;
-            unsigned na = 0u, nb = 0u;
-#pragma unroll 4
-            for (int g = 0; g < F; ++g) { const double pg = mkt[g].p; na += pg < pa ? 1u : 0u; nb += pg < pb ? 1u : 0u; }
+        for (int f0 = c.lane; f0 < F; f0 += 128) {
+            const int f1 = f0 + 32, f2 = f0 + 64, f3 = f0 + 96;
+            const double pa = mkt[f0].p, pb = f1 < F ? mkt[f1].p : 0.0, pc = f2 < F ? mkt[f2].p : 0.0,
+                         pd = f3 < F ? mkt[f3].p : 0.0;
+            unsigned na = 0u, nb = 0u, nc = 0u, nd = 0u;
+#pragma unroll 2
+            for (int g = 0; g < F; ++g) {
+                const double pg = mkt[g].p;
+                na += pg < pa ? 1u : 0u; nb += pg < pb ? 1u : 0u; nc += pg < pc ? 1u : 0u; nd += pg < pd ? 1u : 0u;
+            }
             mkt[f0].cls = na;
             if (f1 < F) mkt[f1].cls = nb;
+            if (f2 < F) mkt[f2].cls = nc;
+            if (f3 < F) mkt[f3].cls = nd;
         }
     }
     if (last >= 15) {
@@ -505,8 +511,11 @@ __device__ void phase_produce(Ctx &c)
             c.kf(K_interests)[i] = interests; c.kf(K_wages)[i] = wages;
             double Pl = 0.0;
             if (Y > 0.0) Pl = (1.01 * ((wages + interests) + theta * deb)) / Y;
-            if (c.kf(K_P)[i] < Pl) c.kf(K_P)[i] = Pl;
-            c.kf(K_Q)[i] = 0.0; c.kf(K_Yd)[i] = 0.0;
+            double P = c.kf(K_P)[i];
+            if (P < Pl) { P = Pl; c.kf(K_P)[i] = P; }
+            // the Q slot carries 1 / P through the capital-goods market (MODEL.md 4.5); K-firm
+            // sales are Yavail - stock, written by the accounting phase
+            c.kf(K_Q)[i] = 1.0 / P; c.kf(K_Yd)[i] = 0.0;
         }
     }
     __syncwarp();
@@ -522,7 +531,8 @@ __device__ void phase_capital_market(Ctx &c)
     const int F = L.F, N = L.N, lane = c.lane;
     const int z = c.z_k() < N ? c.z_k() : N;
     Order ord; ord.init(c.d, MKT_CAP, c.a->od[MKT_CAP], c.okeys(), lane);
-    double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Qk = c.kf(K_Q), *Ysk = c.at(L.s_kYstock);
+    double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Ysk = c.at(L.s_kYstock);
+    const double *RPk = c.kf(K_Q);   // 1 / P, parked there by phase_produce
     double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
     double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
     int *buyers = c.iat(L.s_ic);
@@ -560,25 +570,23 @@ __device__ void phase_capital_market(Ctx &c)
                 for (int k = 0; k < ZM; ++k) {
                     if (k < z && cb > 0.0 && kd > 0.0) {
                         const int best = cand[k];
-                        const double pk = pr[k];
-                        const double afford = cb / pk;
+                        const double pk = pr[k], rpk = RPk[best];
+                        const double afford = cb * rpk;
                         const double want = afford < kd ? afford : kd;
                         Ydk[best] = Ydk[best] + want;
                         const double ys = Ysk[best];
                         if (ys > 0.0) {
                             const double full = kd * pk;
                             const double spend = cb < full ? cb : full;
-                            const double q = spend / pk;
+                            const double q = spend * rpk;
                             if (ys > q) {
                                 Ysk[best] = ys - q;
-                                Qk[best] = Qk[best] + q;
                                 kd = kd - q; cb = cb - spend;
                                 lq = lq - spend; iv = iv + q; vi = vi + spend;
                             } else {
                                 const double cost = ys * pk;
                                 kd = kd - ys; cb = cb - cost;
                                 lq = lq - cost;
-                                Qk[best] = Qk[best] + ys;
                                 iv = iv + ys; vi = vi + cost;
                                 Ysk[best] = 0.0;
                             }
@@ -854,8 +862,11 @@ __device__ void phase_accounting(Ctx &c)
     }
     if (last >= 22) {
         for (int i = c.lane; i < N; i += 32) {
-            double RIC = c.kf(K_P)[i] * c.kf(K_Q)[i];
-            c.kf(K_inv)[i] = (1.0 - c.par()[P_inventory_depreciation]) * c.at(L.s_kYstock)[i];
+            const double left = c.at(L.s_kYstock)[i];
+            const double Qi = c.kf(K_Yavail)[i] - left;   // sold = available - left over
+            c.kf(K_Q)[i] = Qi;
+            double RIC = c.kf(K_P)[i] * Qi;
+            c.kf(K_inv)[i] = (1.0 - c.par()[P_inventory_depreciation]) * left;
             double wages = c.kf(K_wages)[i], interests = c.kf(K_interests)[i];
             double deb = c.kf(K_deb)[i];
             double in = theta * deb;
@@ -1282,6 +1293,10 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
             reinterpret_cast<double *>(img + L.d_kFtot)[i] = c.at(L.s_kFtot)[i];
             reinterpret_cast<double *>(img + L.d_kYstock)[i] = c.at(L.s_kYstock)[i];
         }
+    }
+    if (c.last >= 15 && c.last < 22) {   // debug stop while the K-firm Q slot still carries 1 / P
+        for (int i = c.lane; i < L.N; i += 32) c.kf(K_Q)[i] = 0.0;
+        __syncwarp();
     }
     // smem -> HBM: bulk store of the resident prefix
     fence_proxy_async();

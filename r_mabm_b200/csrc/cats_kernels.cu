@@ -772,8 +772,8 @@ __device__ void phase_goods_market(Ctx &c)
                 const int src = rem ? __ffs(rem) - 1 : 0;
                 const double di = __shfl_sync(FULL, d_t, src);
                 if (rem) {
-                    if (!sold) { if (ys > di) ys = ys - di; else sold = true; }
                     rem &= rem - 1;
+                    if (ys > di) ys = ys - di; else { sold = true; rem = 0u; }   // sold out before my turn: stop replaying
                 }
             }
             const bool full = has && !sold && ys > d_t;

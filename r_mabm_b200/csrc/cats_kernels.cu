@@ -447,7 +447,16 @@ __device__ void phase_job_search(Ctx &c)
 // L2): nobody reads it before the market closes, so no lane ever waits for it.
 // rp = 1 / p: a purchase is b * rp (MODEL.md 4.5).  Sales are what is missing from the stock when
 // the market closes (Q = Y - stock), so the record carries no running total.
-struct __align__(16) MktRec { double ys, rp, p; unsigned cls, spare; };
+// Laid out as three arrays, not one record per seller: 32 lanes reading the class word of 32 random
+// 32-byte records would all land in 4 of the 32 shared-memory banks.
+struct Mkt {
+    double2 *yr;     // [F] stock, 1 / price
+    double *p;       // [F] price
+    unsigned *cls;   // [F] price class
+    __device__ __forceinline__ Mkt(unsigned char *base, int F)
+        : yr(reinterpret_cast<double2 *>(base)), p(reinterpret_cast<double *>(base + 16 * (size_t)F)),
+          cls(reinterpret_cast<unsigned *>(base + 24 * (size_t)F)) {}
+};
 
 // a11 firms_produce! (cats.py:384-385)
 __device__ void phase_produce(Ctx &c)
@@ -456,7 +465,7 @@ __device__ void phase_produce(Ctx &c)
     const int F = L.F, N = L.N, last = c.last;
     const double alpha = c.par()[P_alpha], k = c.par()[P_k], eta = c.par()[P_eta], theta = c.par()[P_theta];
     const double wb = c.scal()[S_wb], pk = c.scal()[S_price_k];
-    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
+    Mkt mkt(c.sm + L.s_U, F);
     for (int f = c.lane; f < F; f += 32) {
         // loads first (see phase_firm_decisions)
         const double K_f = c.cf(C_K)[f], De = c.cf(C_De)[f], deb = c.cf(C_deb)[f], ir_f = c.cf(C_interest_r)[f];
@@ -472,7 +481,7 @@ __device__ void phase_produce(Ctx &c)
         double Pl = 0.0;
         if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
         if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
-        MktRec r; r.ys = Y; r.rp = 1.0 / P; r.p = P; r.cls = 0u; r.spare = 0u; mkt[f] = r;
+        mkt.yr[f] = make_double2(Y, 1.0 / P); mkt.p[f] = P; mkt.cls[f] = 0u;
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
         c.cf(C_Yd)[f] = 0.0;                     // == the all-zero demand accumulator of the goods market
         if (last < 20) c.cf(C_Q)[f] = 0.0;       // else written when the goods market closes
@@ -482,18 +491,18 @@ __device__ void phase_produce(Ctx &c)
         __syncwarp();
         for (int f0 = c.lane; f0 < F; f0 += 128) {
             const int f1 = f0 + 32, f2 = f0 + 64, f3 = f0 + 96;
-            const double pa = mkt[f0].p, pb = f1 < F ? mkt[f1].p : 0.0, pc = f2 < F ? mkt[f2].p : 0.0,
-                         pd = f3 < F ? mkt[f3].p : 0.0;
+            const double pa = mkt.p[f0], pb = f1 < F ? mkt.p[f1] : 0.0, pc = f2 < F ? mkt.p[f2] : 0.0,
+                         pd = f3 < F ? mkt.p[f3] : 0.0;
             unsigned na = 0u, nb = 0u, nc = 0u, nd = 0u;
 #pragma unroll 2
             for (int g = 0; g < F; ++g) {
-                const double pg = mkt[g].p;
+                const double pg = mkt.p[g];
                 na += pg < pa ? 1u : 0u; nb += pg < pb ? 1u : 0u; nc += pg < pc ? 1u : 0u; nd += pg < pd ? 1u : 0u;
             }
-            mkt[f0].cls = na;
-            if (f1 < F) mkt[f1].cls = nb;
-            if (f2 < F) mkt[f2].cls = nc;
-            if (f3 < F) mkt[f3].cls = nd;
+            mkt.cls[f0] = na;
+            if (f1 < F) mkt.cls[f1] = nb;
+            if (f2 < F) mkt.cls[f2] = nc;
+            if (f3 < F) mkt.cls[f3] = nd;
         }
     }
     if (last >= 15) {
@@ -671,7 +680,7 @@ __device__ void phase_goods_market(Ctx &c)
     const int W = L.W, F = L.F, H = L.H, lane = c.lane;
     const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
-    MktRec *mkt = reinterpret_cast<MktRec *>(c.sm + L.s_U);
+    Mkt mkt(c.sm + L.s_U, F);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
     Order ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
     // market constants: computed once, parked in shared memory and re-read per chunk (registers)
@@ -733,7 +742,7 @@ __device__ void phase_goods_market(Ctx &c)
             // key = price class (14 bits) | draw index (3 bits) | seller (14 bits): F <= 16383
 #pragma unroll
             for (int k = 0; k < ZM; ++k)
-                key[k] = k < z ? (mkt[cand[k]].cls << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
+                key[k] = k < z ? (mkt.cls[cand[k]] << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
             sort_keys<ZM>(key);
 #pragma unroll
             for (int k = 0; k < ZM; ++k) {
@@ -753,8 +762,7 @@ __device__ void phase_goods_market(Ctx &c)
                     else {
                         const int cnd = (int)(cp0 & 0xffffull);
                         cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
-                        MktRec *r = &mkt[cnd];
-                        const double2 yr = *reinterpret_cast<const double2 *>(r);   // stock, 1 / price
+                        const double2 yr = mkt.yr[cnd];   // stock, 1 / price
                         fx_red(&acc[cnd], xb);
                         if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; dirty = false; }
                     }
@@ -766,7 +774,7 @@ __device__ void phase_goods_market(Ctx &c)
             const unsigned peers = __match_any_sync(FULL, has ? term : -1 - lane);
             unsigned rem = has ? (peers & lt) : 0u;
             double ys = 0.0;
-            if (has) ys = mkt[term].ys;
+            if (has) ys = mkt.yr[term].x;
             bool sold = false;
             while (__any_sync(FULL, rem != 0u)) {
                 const int src = rem ? __ffs(rem) - 1 : 0;
@@ -787,16 +795,16 @@ __device__ void phase_goods_market(Ctx &c)
                 if (!has) done = true;                    // nothing left to visit: the rest of b is saved
                 else {
                     const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
-                    MktRec *r = &mkt[term];
+                    const int seller = term;
                     if (full) { ys = ys - d_t; b = 0.0; done = true; }
                     else {                                 // lane s: partial fill, then walk on
-                        b = b - ys * r->p; ys = 0.0;
+                        b = b - ys * mkt.p[seller]; ys = 0.0;
                         term = -1;
                         dirty = b > 0.0;
                         done = !dirty;
                         xb = fx_from(b * rpavg);
                     }
-                    if (lastp) r->ys = ys;
+                    if (lastp) mkt.yr[seller].x = ys;
                 }
             } else if (mine && so && has && term == xs) {
                 term = -1; dirty = true;                   // queued behind lane s at the exhausted seller
@@ -813,9 +821,9 @@ __device__ void phase_goods_market(Ctx &c)
     {
         double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
         for (int f = lane; f < F; f += 32) {
-            const MktRec r = mkt[f];
+            const double2 r = mkt.yr[f];
             const unsigned long long a = __ldcg(&acc[f]);
-            Yd[f] = (fx_to(a) * gk[G_price]) * r.rp; Q[f] = c.cf(C_Y_prev)[f] - r.ys;
+            Yd[f] = (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
         }
     }
     __syncwarp();
@@ -828,7 +836,7 @@ __device__ void phase_accounting(Ctx &c)
     const int W = L.W, F = L.F, N = L.N, last = c.last;
     const double delta = c.par()[P_delta], eta = c.par()[P_eta], k = c.par()[P_k], theta = c.par()[P_theta];
     const double divs = c.par()[P_div], taxd = c.par()[P_tax_rate_d];
-    const MktRec *mkt = reinterpret_cast<const MktRec *>(c.sm + L.s_U);
+    const Mkt mkt(c.sm + L.s_U, F);
     double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;   // det_sum partials
     for (int f = c.lane; f < F; f += 32) {
         // loads first (see phase_firm_decisions)
@@ -842,7 +850,7 @@ __device__ void phase_accounting(Ctx &c)
         double dv = 0.0;
         if (Kold != 0.0) dv = (dep * cv) / Kold;
         c.cf(C_capital_value)[f] = (cv - dv) + c.at(L.s_cvalinv)[f];
-        double RIC = mkt[f].p * Q_f;
+        double RIC = mkt.p[f] * Q_f;
         double in = theta * deb;
         double liq = ((((liq0 + RIC) + c.at(L.s_cFtot)[f]) - wages) - interests) - in;
         c.cf(C_deb)[f] = deb - in;
@@ -1273,7 +1281,7 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         // transients image (cats_workset_field_info): Ld vac cFtot cKdem cYstock cvalinv kFtot kYstock
         unsigned char *img = a.debug + (size_t)b * (size_t)L.workset;
         const int nf = L.F + L.N;
-        const MktRec *mkt = reinterpret_cast<const MktRec *>(smem + L.s_U);
+        const Mkt mkt(smem + L.s_U, L.F);
         const bool have_mkt = c.last >= 14;
         for (int i = c.lane; i < L.workset / 4; i += 32) reinterpret_cast<int *>(img)[i] = 0;
         __syncwarp();
@@ -1286,7 +1294,7 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
         for (int f = c.lane; f < L.F; f += 32) {
             reinterpret_cast<double *>(img + L.d_cFtot)[f] = c.at(L.s_cFtot)[f];
             reinterpret_cast<double *>(img + L.d_cKdem)[f] = c.at(L.s_cKdem)[f];
-            reinterpret_cast<double *>(img + L.d_cYstock)[f] = have_mkt ? mkt[f].ys : 0.0;
+            reinterpret_cast<double *>(img + L.d_cYstock)[f] = have_mkt ? mkt.yr[f].x : 0.0;
             reinterpret_cast<double *>(img + L.d_cvalinv)[f] = c.at(L.s_cvalinv)[f];
         }
         for (int i = c.lane; i < L.N; i += 32) {

@@ -125,6 +125,7 @@ class BatchedRollout:
 
     def step(self, train: bool = True):
         actions = self.policy.get_action(self.obs)
+        self.last_actions = actions      # kept for loggers / tests; never leaves the device
         obs, reward, terminated, _ = self.env.step(actions)
         if train:
             self.policy.train(reward, obs, terminated)

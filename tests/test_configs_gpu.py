@@ -1,0 +1,116 @@
+"""GPU parity at the sizes BASELINE.json names (configs 2, 3 and 4), through the C-ABI.
+
+Oracle = the in-repo CPU restatement of docs/MODEL.md ("parity unpinned" w.r.t. ABCredit.jl).
+Bar: int32 state equal, float64 state and statistics equal to the last bit.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from parity_util import bits, compare_state, make_oracles
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(B, **kw):
+    from r_mabm_b200.engine import BatchedCats
+    return BatchedCats(B, **kw)
+
+
+def test_config2_1024_economies_1000_periods_sampled_against_the_oracle():
+    """BASELINE.json config 2: 1,024 default-size economies x 1,000 periods on one GPU.  The oracle
+    runs a sample of the economies (global ids spread over the batch) for the same 1,000 periods;
+    state and the statistics of every period must be identical.  Economy-periods are independent of
+    batch position, so the sample stands for the batch (test_batch_size_and_sharding_invariance)."""
+    B, T = 1024, 1000
+    env = _env(B, seed=2026)
+    ids = [0, 1, 97, 511, 512, 777, 1000, 1023]
+    refs = [orc.OracleEconomy(1000, 100, 20, seed=2026, economy=i) for i in ids]
+    stats_ref = orc.run_batch(refs, T, n_threads=min(len(ids), os.cpu_count() or 1), want_stats=True)
+    stats = torch.cat([env.run(250, want_stats=True) for _ in range(4)], 1)
+    torch.cuda.synchronize()
+    g = stats[ids].cpu().numpy()
+    assert g.shape == stats_ref.shape == (len(ids), T, 16)
+    assert np.array_equal(bits(g), bits(stats_ref))
+
+    class Sub:   # the sampled economies of the batch, presented like a small batch
+        W, F, N = env.W, env.F, env.N
+
+        @staticmethod
+        def field(name):
+            return env.field(name)[ids]
+    assert compare_state(Sub, refs, "t=1000") == []
+    un = stats[:, -200:, 2]
+    assert 0.0 < float(un.mean()) < 0.5 and torch.isfinite(stats).all()
+
+
+def test_config3_monte_carlo_seeds_64_macro_aggregates_agree():
+    """north_star: fresh-RNG runs agree on macro aggregates across 64 seeds.  With the counter-based
+    generator the agreement is exact, so the distributions (mean / spread of Y_real, Un,
+    inflationRate over 64 seeds) coincide to the last bit as well."""
+    W, F, N, T = 300, 30, 6, 120
+    seeds = list(range(64))   # one Philox stream per global economy id: 64 independent seeds
+    env = _env(64, W=W, F=F, N=N, seed=99)
+    stats = env.run(T, want_stats=True)
+    torch.cuda.synchronize()
+    refs = [orc.OracleEconomy(W, F, N, seed=99, economy=i) for i in seeds]
+    stats_ref = orc.run_batch(refs, T, n_threads=os.cpu_count() or 1, want_stats=True)
+    g = stats.cpu().numpy()
+    for col in (0, 2, 7):   # Y_real, Un, inflationRate
+        assert np.array_equal(bits(g[:, :, col]), bits(stats_ref[:, :, col]))
+        tail_g, tail_r = g[:, -40:, col].mean(1), stats_ref[:, -40:, col].mean(1)
+        assert tail_g.mean() == tail_r.mean() and tail_g.std() == tail_r.std()
+    # the seeds really are different economies
+    assert len({float(x) for x in g[:, -1, 0]}) == 64
+
+
+def test_config4_marl_rollout_env_policy_and_td_update_on_device():
+    """BASELINE.json config 4 (examples/agent_training.py: CatsLog, 2 learned firms): the batched
+    rollout keeps observations, actions and rewards on the device.  Every step is checked against
+    the oracle stepping the same economies with the actions the device policy chose, and the Q
+    tables against the scalar TD(0) rule (/root/reference/rmabm/agents/qlearners.py:156-166)."""
+    from r_mabm_b200.environments import CatsLog
+    BL = dict(CatsLog._default_gym_spaces_bounds)
+    from r_mabm_b200.rollout import BatchedQPolicy, BatchedRollout
+    B, A, W, F, N = 6, 2, 300, 30, 6
+    env = _env(B, W=W, F=F, N=N, n_agents=A, log_mode=True, seed=31)
+    pol = BatchedQPolicy(B, A, BL, alpha=0.1, gamma=0.99, epsilon=0.5, device="cuda", seed=3)
+    ro = BatchedRollout(env, pol, t_burnin=20, T=10)
+    obs0 = ro.reset(seed=31).clone()
+    refs = make_oracles(B, W, F, N, seed=31)
+    for o in refs:
+        for _ in range(20):
+            o.step()
+    first = [o.step(actions=[[1.0, 1.0]] * A, mask=[0] * A, flags=orc.FLAG_LOG | orc.FLAG_BURNIN)[0] for o in refs]
+    assert np.array_equal(bits(obs0.cpu().numpy()), bits(np.stack(first)))
+    launches0 = env._lib.cats_launch_count()
+    for t in range(10):
+        q_before = pol.Q.clone()
+        obs_prev = ro.obs.clone()
+        reward, term = ro.step(train=True)
+        torch.cuda.synchronize()
+        s0, s1, a0, a1 = [x.cpu().numpy() for x in pol._last]
+        lo0, hi0 = BL["act_production_factor"]; lo1, hi1 = BL["act_price_factor"]
+        acts = ro.last_actions.cpu().numpy()
+        assert np.allclose(acts, np.stack([lo0 + a0 * (hi0 - lo0) / 10, lo1 + a1 * (hi1 - lo1) / 10], -1), rtol=0, atol=1e-15)
+        for b, o in enumerate(refs):
+            r_obs, r_rew = o.step(actions=acts[b], mask=[1] * A, flags=orc.FLAG_LOG)
+            assert np.array_equal(bits(ro.obs[b].cpu().numpy()), bits(r_obs)), (t, b)
+            assert np.array_equal(bits(reward[b].cpu().numpy()), bits(r_rew)), (t, b)
+        # TD(0) on exactly one cell per (economy, agent)
+        n0, n1 = [x.cpu().numpy() for x in pol.bin_obs(ro.obs)]
+        qb, qa = q_before.cpu().numpy(), pol.Q.cpu().numpy()
+        changed = (qb != qa).sum()
+        assert changed <= B * A
+        for b in range(B):
+            for a in range(A):
+                cur = qb[b, a, s0[b, a], s1[b, a], a0[b, a], a1[b, a]]
+                boot = 0.0 if term[b] else 0.99 * qb[b, a, n0[b, a], n1[b, a]].max()
+                want = cur + 0.1 * ((float(reward[b, a]) + boot) - cur)
+                assert qa[b, a, s0[b, a], s1[b, a], a0[b, a], a1[b, a]] == pytest.approx(want, rel=1e-15, abs=1e-15)
+        del obs_prev
+    assert env._lib.cats_launch_count() - launches0 == 10     # one period-kernel launch per rollout step
+    assert compare_state(env, refs, "after rollout") == []

@@ -135,10 +135,10 @@ size_t cats_workset_bytes(int W, int F, int N);
 int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset,
                             int32_t *count, int32_t *dtype);
 
-/* Launch geometry actually used for (W,F,N): threads per block, dynamic shared bytes,
- * resident blocks per SM (occupancy query).  For DESIGN.md / bench.py reporting. */
+/* Launch geometry actually used for (W,F,N): threads per block (32 per economy, several economies
+ * per block), dynamic shared bytes per block, economies resident per SM, number of SMs. */
 int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
-                     int32_t *blocks_per_sm, int32_t *num_sms);
+                     int32_t *economies_per_sm, int32_t *num_sms);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t cats_launch_count(void);

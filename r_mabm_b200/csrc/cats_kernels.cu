@@ -58,6 +58,8 @@ struct KArgs {
     int stop_phase;
     unsigned char *debug;
     long long *cycles;  // debug: [16] per-phase clock64 totals of block 0
+    int slice;          // bytes of shared memory per economy (Layout::smem rounded up to 128)
+    int bars;           // 1: the block re-aligns before the accounting phases (0 under stop_phase)
 };
 
 // per-warp view of the working set.  Only two base pointers are kept: every section address is
@@ -1130,14 +1132,14 @@ __device__ void phase_closing(Ctx &c)
 
 // ---------------------------------------------------------------------------------------------
 // one period; phase ids as docs/MODEL.md section 6 (stop_phase halts after the given id)
-template <int ZM>
+template <int ZM, int G>
 __device__ void run_period(Ctx &c)
 {
     const KArgs &a = *c.a;
     const int F = a.L.F, N = a.L.N, last = c.last;
 #ifdef CATS_PROFILE_PHASES
     long long t0 = 0;
-    const bool prof = a.cycles && c.lane == 0 && blockIdx.x == 0;
+    const bool prof = a.cycles && c.lane == 0 && c.b == 0;
     if (prof) t0 = clock64();
 #define TICK(slot) do { if (prof) { long long t1 = clock64(); a.cycles[slot] += t1 - t0; t0 = t1; } } while (0)
 #else
@@ -1177,6 +1179,9 @@ __device__ void run_period(Ctx &c)
     phase_goods_market<ZM>(c);  // 18, 19, 20
     TICK(6);
     if (last < 21) return;
+    // the goods market is where economies drift apart (its round count differs); the closing phases
+    // are a long stretch of once-per-period code again: back in step before them
+    if (G > 1 && a.bars) __syncthreads();
     phase_accounting(c);      // 21, 22
     TICK(7);
     if (last < 23) return;
@@ -1195,18 +1200,31 @@ __device__ void run_period(Ctx &c)
 #undef TICK
 }
 
-template <int ZM, int MINB>
-__global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
+// G economies per block, one warp each, every warp on its own slice of the block's shared memory.
+// The warps of a block never exchange data; they share a block so that they START TOGETHER: economies
+// of one size take the same path through the ~170 KB of period code at nearly the same pace, and warps
+// that run in step fetch each instruction line once for all of them.  One-warp blocks are rescheduled
+// one by one and spread over all phases, which costs a quarter of the throughput in instruction-cache
+// misses ("instruction supply").  Multi-period launches re-align at every period.
+template <int ZM, int G, int MINB>
+__global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem_block[];
     const Layout &L = a.L;
+    unsigned char *smem = smem_block + (size_t)(threadIdx.x >> 5) * (size_t)a.slice;
     Ctx c;
     c.sm = smem; c.a = &a;
-    c.lane = threadIdx.x;
+    c.lane = threadIdx.x & 31;
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 16);
-    const long long b = blockIdx.x;
-    if (b >= a.B) return;
+    const long long b = (long long)blockIdx.x * G + (threadIdx.x >> 5);
+    if (b >= a.B) {
+        if (G > 1) for (int t = 0; t < a.n_periods; ++t) {   // keep the block's barrier count
+            if (t > 0) __syncthreads();
+            if (a.bars) __syncthreads();
+        }
+        return;
+    }
     c.b = b;
     unsigned char *blob = a.blobs + (size_t)b * (size_t)L.blob;
     c.blob = blob;
@@ -1237,9 +1255,10 @@ __global__ void __launch_bounds__(32, MINB) cats_period_kernel(const __grid_cons
     c.d.tape_z = a.tape_z;
 
     for (int t = 0; t < a.n_periods; ++t) {
+        if (G > 1 && t > 0) __syncthreads();   // back in step (see above)
         c.d.period = (uint32_t)c.scal()[S_timestep];
         c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
-        run_period<ZM>(c);
+        run_period<ZM, G>(c);
         __syncwarp();
         if (a.stats && c.lane < N_STATS) {
             const double *s = c.scal();
@@ -1367,10 +1386,60 @@ constexpr int kThreads = 32;    // one warp per economy
 #endif
 constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
 typedef void (*KernelFn)(const KArgs);
-static KernelFn select_kernel(int max_z)
+// development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
+static int smem_pad()
 {
-    if (max_z > 0 && max_z <= 5) return cats_period_kernel<5, kMinBlocks>;
-    return cats_period_kernel<MAX_Z, kMinBlocks>;
+    static int pad = -1;
+    if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
+    return pad;
+}
+template <int ZM>
+static KernelFn select_group(int g)
+{
+    switch (g) {
+    case 2: return cats_period_kernel<ZM, 2, kMinBlocks / 2>;
+    case 4: return cats_period_kernel<ZM, 4, kMinBlocks / 4>;
+    case 8: return cats_period_kernel<ZM, 8, kMinBlocks / 8>;
+    case 12: return cats_period_kernel<ZM, 12, kMinBlocks / 12>;
+    default: return cats_period_kernel<ZM, 1, kMinBlocks>;
+    }
+}
+static KernelFn select_kernel(int max_z, int g)
+{
+    if (max_z > 0 && max_z <= 5) return select_group<5>(g);
+    return select_group<MAX_Z>(g);
+}
+static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 127) & ~127; }
+// Economies per block (see cats_period_kernel).  Shared memory and the register file bound how many
+// economies fit on an SM (at most kMinBlocks).  The launch takes as long as its busiest SM; a period
+// on an SM with n resident economies costs about (12 + n) units (measured: latency + contention), and
+// economies that run in step save instruction fetches (measured factors below).  The cheapest shape
+// wins.  CATS_GROUP=<1|2|4|8|12> overrides (development aid).
+static int choose_group(const Layout &L, long long B, int sms)
+{
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("CATS_GROUP"); forced = e ? atoi(e) : 0; }
+    const int slice = slice_bytes(L);
+    const int sm_bytes = 228 * 1024, block_max = 227 * 1024, reserve = 1024;
+    const int cand[5] = {12, 8, 4, 2, 1};
+    if (sms < 1) sms = 1;
+    int best = 1; double best_score = 1e300;
+    for (int i = 0; i < 5; ++i) {
+        const int g = cand[i];
+        if (g > 1 && g * slice > block_max) continue;
+        if (forced == g) return g;
+        long long fit = sm_bytes / (g * (long long)slice + reserve);     // blocks resident per SM
+        if (fit > kMinBlocks / g) fit = kMinBlocks / g;
+        if (fit < 1) fit = 1;
+        const long long blocks = (B + g - 1) / g;
+        long long per_sm = (blocks + sms - 1) / sms;                     // blocks on the busiest SM ...
+        const double waves = (double)per_sm / (double)fit;               // ... in this many rounds of `fit`
+        if (per_sm > fit) per_sm = fit;
+        const double step[5] = {0.62, 0.68, 0.75, 0.85, 1.0};             // g = 12, 8, 4, 2, 1
+        const double score = (waves > 1.0 ? waves : 1.0) * (12.0 + (double)(per_sm * g)) * step[i];
+        if (score < best_score) { best_score = score; best = g; }
+    }
+    return best;
 }
 
 static int fail(int code, const char *fmt, const char *detail)
@@ -1481,22 +1550,15 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
     return CATS_OK;
 }
 
-// development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
-static int smem_pad()
-{
-    static int pad = -1;
-    if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
-    return pad;
-}
 
-static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, int *num_sms)
+static int configure_kernel(const Layout &L, KernelFn fn, int g, int *blocks_per_sm, int *num_sms)
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int smem = L.smem + smem_pad();
+    const int smem = slice_bytes(L) * g;
     if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1505,12 +1567,12 @@ static int configure_kernel(const Layout &L, KernelFn fn, int *blocks_per_sm, in
     e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads * g, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (occ < 1) return fail(CATS_ESMEM, "kernel cannot be resident with this working set%s", "");
-    *blocks_per_sm = occ; *num_sms = sms;
+    *blocks_per_sm = occ * g; *num_sms = sms;   // economies resident per SM
     return CATS_OK;
 }
 
@@ -1520,9 +1582,12 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
     if (int rc = check_sizes(W, F, N)) return rc;
     Layout L = make_layout(W, F, N);
     int occ = 0, sms = 0;
-    if (int rc = configure_kernel(L, select_kernel(5), &occ, &sms)) return rc;
-    if (threads) *threads = kThreads;
-    if (smem_bytes) *smem_bytes = L.smem;
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int g = choose_group(L, 1ll << 40, nsm);   // the shape of a launch that fills the GPU
+    if (int rc = configure_kernel(L, select_kernel(5, g), g, &occ, &sms)) return rc;
+    if (threads) *threads = kThreads * g;            // per block: g economies, one warp each
+    if (smem_bytes) *smem_bytes = slice_bytes(L) * g;
     if (blocks_per_sm) *blocks_per_sm = occ;
     if (num_sms) *num_sms = sms;
     return CATS_OK;
@@ -1581,11 +1646,14 @@ int cats_step(const cats_step_args *s)
         a.tape_z[0] = s->tape_z[0]; a.tape_z[1] = s->tape_z[1]; a.tape_z[2] = s->tape_z[2];
     }
     int occ = 0, sms = 0;
-    KernelFn fn = select_kernel(s->max_z);
-    if (int rc = configure_kernel(a.L, fn, &occ, &sms)) return rc;
-    // one block (= one warp) per economy: the hardware block scheduler balances economies of
-    // different length over the SMs; `occ` of them are resident per SM
-    fn<<<(unsigned)s->B, kThreads, a.L.smem + smem_pad(), (cudaStream_t)s->stream>>>(a);
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int g = choose_group(a.L, s->B, nsm);
+    a.slice = slice_bytes(a.L);
+    a.bars = s->stop_phase ? 0 : 1;
+    KernelFn fn = select_kernel(s->max_z, g);
+    if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
+    fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));

@@ -273,7 +273,8 @@ class BatchedCats:
         with torch.cuda.device(self.device):
             nat.check(self._lib.cats_launch_info(self.W, self.F, self.N, C.byref(t), C.byref(s),
                                                  C.byref(b), C.byref(n)))
-        return {"threads": t.value, "smem_bytes": s.value, "blocks_per_sm": b.value, "num_sms": n.value}
+        return {"threads_per_block": t.value, "economies_per_block": t.value // 32, "smem_bytes_per_block": s.value,
+                "economies_per_sm": b.value, "num_sms": n.value}
 
     def algo_bytes_per_period(self) -> int:
         """CATS_ALGO_BYTES (docs/DESIGN.md): every state byte read once and written once."""

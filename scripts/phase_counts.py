@@ -16,4 +16,4 @@ nat.load().cats_debug_phase_cycles(None)
 names = ["firm", "fire", "job", "produce", "capital", "income+budget", "goods", "accounting", "reward", "tracking", "bankrupt", "closing"]
 c = cyc.cpu().numpy() / periods
 print("cycles/period:", {n: int(v) for n, v in zip(names, c[:12])}, "total", int(c[:12].sum()))
-print(f"goods market per period: rounds {c[12]:.1f}, walk iterations {c[13]:.1f}, replay iterations {c[14]:.1f}")
+print(f"goods market cycles per period: prepare {c[12]:.0f}, walk {c[13]:.0f}, match+replay {c[14]:.0f}, commit {c[15]:.0f}")

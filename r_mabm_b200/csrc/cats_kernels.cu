@@ -1401,6 +1401,7 @@ static KernelFn select_group(int g)
     case 4: return cats_period_kernel<ZM, 4, kMinBlocks / 4>;
     case 8: return cats_period_kernel<ZM, 8, kMinBlocks / 8>;
     case 12: return cats_period_kernel<ZM, 12, kMinBlocks / 12>;
+
     default: return cats_period_kernel<ZM, 1, kMinBlocks>;
     }
 }

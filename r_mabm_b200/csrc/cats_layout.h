@@ -99,10 +99,10 @@ inline Layout make_layout(int W, int F, int N)
     L.s_kFtot = (int32_t)o; o += L.rowN;
     L.s_kYstock = (int32_t)o; o += L.rowN;
     L.s_ic = (int32_t)o; o += up16(4ll * (F + N));
-    L.s_bad = (int32_t)o; o += up16(F + N);
-    // union region: F seller records of 32 B | firing pool of {worker, key} pairs | job seekers
+    L.s_bad = L.s_ic;   // bankrupt flags reuse the firing / capital-market scratch (idle by then)
+    // union region: goods-market seller table | firing pool of {worker, key} pairs | job seekers
     // (one uint16 per worker: W <= 65535 in this build)
-    int64_t u = 32ll * F;
+    int64_t u = 28ll * F;   // seller table: (stock, 1/price) 16 B + price 8 B + class 4 B
     if (2ll * W > u) u = 2ll * W;
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;

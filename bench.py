@@ -72,7 +72,33 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _run_nvml(self) -> bool:
+        """Same fields through NVML (a query takes microseconds, so short timed regions get many samples)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self._halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active"
+                                                       for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            self._halt.wait(0.02)
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -121,9 +147,15 @@ def cpu_baseline(sample_economies=256, sample_periods=200, burnin=BURNIN, thread
     t0 = time.perf_counter()
     orc.run_batch(econs, sample_periods, n_threads=threads, want_stats=False)
     dt = time.perf_counter() - t0
+    # the reference steps ONE economy on ONE thread (Python + juliacall): the like-for-like figure
+    t0 = time.perf_counter()
+    orc.run_batch(econs[:4], 50, n_threads=1, want_stats=False)
+    one = 4 * 50 / (time.perf_counter() - t0)
     return {"value": sample_economies * sample_periods / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "single_thread_value": one,
             "sample": f"{sample_economies} default-size economies x {sample_periods} periods after {burnin} burn-in "
-                      f"periods, C oracle (gcc -O2), OpenMP over economies, {threads} threads"}
+                      f"periods, C oracle (gcc -O2), OpenMP over economies, {threads} threads; single_thread_value: "
+                      f"4 of them x 50 periods on 1 thread"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1161,7 +1161,6 @@ __device__ void run_period(Ctx &c)
     __syncwarp();
     TICK(1);
     if (last < 13) return;
-    if (c.lane == 0 && last >= 18) bulk_prefetch_l2(c.blob + a.L.o_PA, (uint32_t)(a.L.blob - a.L.o_PA));
     phase_job_search<ZM>(c);  // 13
     __syncwarp();
     TICK(2);
@@ -1170,6 +1169,9 @@ __device__ void run_period(Ctx &c)
     TICK(3);
     if (last < 16) return;
     phase_capital_market<ZM>(c);  // 16
+    // household wealth / permanent income are first touched by the goods market: into L2 just ahead
+    // of it (any earlier and the lines age out of L2 again before they are used)
+    if (c.lane == 0 && last >= 18) bulk_prefetch_l2(c.blob + a.L.o_PA, (uint32_t)(a.L.blob - a.L.o_PA));
     TICK(4);
     if (last < 17) return;
     phase_gov_income(c);      // 17 (+ government side of 18)
@@ -1401,6 +1403,7 @@ static KernelFn select_group(int g)
     case 4: return cats_period_kernel<ZM, 4, kMinBlocks / 4>;
     case 8: return cats_period_kernel<ZM, 8, kMinBlocks / 8>;
     case 12: return cats_period_kernel<ZM, 12, kMinBlocks / 12>;
+
 
     default: return cats_period_kernel<ZM, 1, kMinBlocks>;
     }

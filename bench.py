@@ -71,29 +71,30 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self._nv = None
+        try:   # NVML set up here, outside the timed region: the thread only polls
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+            bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+            self._nv = (nv, h, bits, nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
 
     def _run_nvml(self) -> bool:
         """Same fields through NVML (a query takes microseconds, so short timed regions get many samples)."""
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
-                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        except Exception:
+        if self._nv is None:
             return False
+        nv, h, bits, mx = self._nv
         while not self._halt.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active"
-                                                       for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
             except Exception:
                 pass
-            self._halt.wait(0.02)
+            self._halt.wait(0.01)
         return True
 
     def run(self):

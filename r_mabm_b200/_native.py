@@ -32,7 +32,7 @@ EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
     "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
-    "cats_launch_count", "cats_debug_phase_cycles",
+    "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group",
 ]
 
 
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     L.cats_launch_count.restype = C.c_uint64
     L.cats_debug_phase_cycles.argtypes = [C.c_void_p]
     L.cats_debug_phase_cycles.restype = None
+    L.cats_debug_set_group.argtypes = [C.c_int]
+    L.cats_debug_set_group.restype = None
     if L.cats_abi_version() != 1:
         raise ImportError(f"{LIB_PATH}: ABI version {L.cats_abi_version()} != 1; rebuild")
     _lib = L

@@ -1382,6 +1382,7 @@ using namespace cats;
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
+static int g_group = 0;                // debug: set by cats_debug_set_group() (0 = automatic)
 constexpr int kThreads = 32;    // one warp per economy
 #ifndef CATS_MIN_BLOCKS
 #define CATS_MIN_BLOCKS 24
@@ -1421,8 +1422,9 @@ static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 127) &
 // wins.  CATS_GROUP=<1|2|4|8|12> overrides (development aid).
 static int choose_group(const Layout &L, long long B, int sms)
 {
-    static int forced = -1;
-    if (forced < 0) { const char *e = getenv("CATS_GROUP"); forced = e ? atoi(e) : 0; }
+    static int env_forced = -1;
+    if (env_forced < 0) { const char *e = getenv("CATS_GROUP"); env_forced = e ? atoi(e) : 0; }
+    const int forced = g_group ? g_group : env_forced;
     const int slice = slice_bytes(L);
     const int sm_bytes = 228 * 1024, block_max = 227 * 1024, reserve = 1024;
     const int cand[5] = {12, 8, 4, 2, 1};
@@ -1481,6 +1483,7 @@ int cats_abi_version(void) { return CATS_ABI_VERSION; }
 const char *cats_last_error(void) { return g_err; }
 uint64_t cats_launch_count(void) { return g_launches.load(); }
 void cats_debug_phase_cycles(void *d_cycles16) { g_cycles = (long long *)d_cycles16; }
+void cats_debug_set_group(int economies_per_block) { g_group = economies_per_block; }
 
 size_t cats_blob_bytes(int W, int F, int N)
 {

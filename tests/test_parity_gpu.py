@@ -77,3 +77,28 @@ def test_batch_size_and_sharding_invariance():
     part.run(15)
     torch.cuda.synchronize()
     assert torch.equal(full.blobs[3:5], part.blobs)
+
+
+def test_block_shape_never_changes_results():
+    """Economies per block is a scheduling choice: 1, 2, 4, 8 and 12 per block, with
+    a ragged last block and with the per-period barriers of a multi-period launch, give the same bits."""
+    from r_mabm_b200 import _native as nat
+    from r_mabm_b200.engine import BatchedCats
+    lib = nat.load()
+    ref = None
+    try:
+        for g in (1, 2, 4, 8, 12, 0):
+            lib.cats_debug_set_group(g)
+            env = BatchedCats(29, W=200, F=20, N=5, n_agents=1, seed=11)
+            env.run(7)
+            acts = torch.full((29, 1, 2), 1.02, dtype=torch.float64, device="cuda")
+            env.step(acts, torch.ones((29, 1), dtype=torch.uint8, device="cuda"))
+            stats = env.run(5, want_stats=True)
+            torch.cuda.synchronize()
+            got = (env.blobs.clone(), stats.clone())
+            if ref is None:
+                ref = got
+            else:
+                assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), f"group {g}"
+    finally:
+        lib.cats_debug_set_group(0)

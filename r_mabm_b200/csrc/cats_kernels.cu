@@ -1245,8 +1245,10 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
     for (int i = c.lane; i < N_PARAMS; i += 32) c.par()[i] = pr[i];
     if (c.lane == 0) c.par()[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
-    // zero the transients (debug images are deterministic; the queue masks must start clear)
-    for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
+    // every transient is written before it is read within a period; only a debug image of a period
+    // stopped half-way shows the ones not reached yet, and those must read as zero
+    if (a.debug)
+        for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
     __syncwarp();
     mbar_wait(bar, 0);
     __syncwarp();

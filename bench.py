@@ -281,12 +281,21 @@ def run_b200(args):
         algo = env.algo_bytes_per_period() * B              # bytes per launch on this GPU
         avg_launch_s = (sum(per_launch_ms) / len(per_launch_ms)) * 1e-3
         achieved = algo / avg_launch_s / 1e9
-        traffic = None
+        traffic, issue = None, None
         tp = ROOT / "profiles" / "roofline_traffic.json"
         if tp.exists():
             try:
                 tj = json.loads(tp.read_text())
                 traffic = tj.get("dram_bytes_per_economy_period", 0) * B or None
+                # what actually bounds the kernel: warp-instruction issue.  Instruction
+                # count per economy-period from the committed ncu capture, rate measured here.
+                wi = tj.get("warp_instructions_per_economy_period")
+                if wi and clocks and clocks.get("sm_mhz"):
+                    sms = env.launch_info()["num_sms"]
+                    peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6
+                    issue = {"warp_instructions_per_economy_period": wi, "achieved_ginst_s": B / avg_launch_s * wi / 1e9,
+                             "peak_ginst_s": peak_issue / 1e9, "frac": (B / avg_launch_s * wi) / peak_issue,
+                             "source": "profiles/roofline_traffic.json (ncu) x rate measured in this run"}
             except Exception:
                 traffic = None
         line = {
@@ -300,7 +309,9 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algo_bytes_per_economy_period": env.algo_bytes_per_period(),
-                         "note": "latency-bound serial matching markets, not bandwidth-bound; see DESIGN.md"},
+                         "issue_slots": issue,
+                         "note": "bound by dependent-instruction latency and issue slots of the serial matching "
+                                 "markets, not by bandwidth; see DESIGN.md 2.3"},
             "clocks": clocks, "launch": env.launch_info(), "mean_unemployment_check": un_mean,
         }
         if not args.no_cpu_baseline:

@@ -255,6 +255,26 @@ struct Order {
         } while (x >= n);
         return (int)x;
     }
+    // inverse of at(): the position at which agent `who` is visited (Feistel rounds undone in reverse
+    // order, cycle-walked the same way).  Only for the keyed bijection, not for a tape order.
+    __device__ __forceinline__ int position_of(int who) const
+    {
+        const uint32_t a = k->a, b = k->b, m = k->m, n = k->n;
+        const uint32_t k0 = k->k[0], k1 = k->k[1], k2 = k->k[2], k3 = k->k[3];
+        uint32_t x = (uint32_t)who;
+        do {
+            uint32_t L = b > 1 ? __umulhi(x, m) : x;
+            uint32_t R = x - L * b;
+            uint32_t t;
+            t = __umulhi(perm_hash(L, k3), b); R = R >= t ? R - t : R + b - t;
+            t = __umulhi(perm_hash(R, k2), a); L = L >= t ? L - t : L + a - t;
+            t = __umulhi(perm_hash(L, k1), b); R = R >= t ? R - t : R + b - t;
+            t = __umulhi(perm_hash(R, k0), a); L = L >= t ? L - t : L + a - t;
+            x = L * b + R;
+        } while (x >= n);
+        return (int)x;
+    }
+    __device__ __forceinline__ bool from_tape() const { return k->tape_order != nullptr; }
 };
 
 // stable ascending sort of ZM (candidate, price) pairs by price, register only: a sorting network

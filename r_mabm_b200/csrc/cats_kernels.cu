@@ -98,6 +98,7 @@ struct Ctx {
 };
 
 enum { M_STATUS = 0 };
+constexpr int JOB_SORT_MAX = 128;   // job search: up to this many seekers are sorted by position (see phase_job_search)
 
 __device__ __forceinline__ double bfly(double a)
 {
@@ -390,7 +391,44 @@ __device__ void phase_job_search(Ctx &c)
     Order ord; ord.init(c.d, MKT_JOB, c.a->od[MKT_JOB], c.okeys(), lane);
     unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
     int total = 0;
-    for (int base = 0; base < W; base += 128) {
+    // Few seekers (the usual case: unemployment of a few percent): list them with one coalesced pass
+    // over the employment links, ask the visiting order for each one's POSITION (the inverse
+    // bijection) and sort the handful by position -- instead of evaluating the order at all W
+    // positions and gathering W links in that order.  Same visiting order, by construction.
+    bool listed = false;
+    const int cap3 = L.U_bytes / 6;   // three uint16 arrays: seekers in visiting order | by index | positions
+    if (!ord.from_tape()) {
+        unsigned short *byidx = seekers + cap3, *posv = seekers + 2 * cap3;
+        int U = 0;
+        for (int base = 0; base < W; base += 128) {
+            int oc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int w = base + 32 * q + lane; oc[q] = w < W ? c.Oc()[w] : 0; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool un = oc[q] < 0;
+                const unsigned bal = __ballot_sync(FULL, un);
+                const int at = U + __popc(bal & c.lt());
+                if (un && at < cap3) byidx[at] = (unsigned short)(base + 32 * q + lane);
+                U += __popc(bal);
+            }
+        }
+        if (U <= JOB_SORT_MAX && U <= cap3) {
+            __syncwarp();
+            for (int i = lane; i < U; i += 32) posv[i] = (unsigned short)ord.position_of((int)byidx[i]);
+            __syncwarp();
+            for (int i = lane; i < U; i += 32) {
+                const unsigned mine = posv[i];
+                int r = 0;
+                for (int j = 0; j < U; ++j) r += posv[j] < mine ? 1 : 0;   // positions are distinct
+                seekers[r] = byidx[i];
+            }
+            total = U;
+            listed = true;
+        }
+        __syncwarp();
+    }
+    for (int base = 0; !listed && base < W; base += 128) {
         int w[4]; int oc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

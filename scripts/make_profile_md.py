@@ -43,5 +43,8 @@ out += ["", "Per source function (instructions per economy-period, share of stal
 open(f"profiles/{tag}_ncu_period_kernel.md", "w").write("\n".join(out) + "\n")
 json.dump({"kernel": kern, "source": f"profiles/{tag}_ncu_period_kernel.md (ncu --set full, {int(nep)} economies x 1 period)",
            "dram_bytes_read": dr, "dram_bytes_write": dw, "economy_periods": nep,
-           "dram_bytes_per_economy_period": (dr + dw) / nep}, open("profiles/roofline_traffic.json", "w"), indent=1)
+           "dram_bytes_per_economy_period": (dr + dw) / nep,
+           "warp_instructions_per_economy_period": inst / nep,
+           "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active")},
+          open("profiles/roofline_traffic.json", "w"), indent=1)
 print("\n".join(out[:48]))

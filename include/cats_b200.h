@@ -130,6 +130,11 @@ int cats_step_host(const cats_step_args *args_with_host_io, void *d_scratch);
 
 /* Size of the on-chip working set image written to d_debug (blob + transients). */
 size_t cats_workset_bytes(int W, int F, int N);
+/* Element stride of a named state field, in elements of its dtype: 1 for contiguous rows, 2 for
+ * "PA" and "perm" (households are stored as {PA, perm} records: element i of the field lives at
+ * byte_offset + i * stride * sizeof(dtype)).  0 for an unknown name. */
+int cats_field_stride(const char *name);
+
 /* Describe a transient field inside the working-set image (same contract as cats_field_info).
  * Names: c_Ld c_vac k_Ld k_vac (i32), c_Ftot c_Kdem c_Ystock c_valinv k_Ftot k_Ystock (f64). */
 int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset,

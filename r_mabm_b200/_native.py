@@ -30,6 +30,7 @@ STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_t
 # every symbol include/cats_b200.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
+    "cats_field_stride",
     "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
     "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group",
@@ -73,6 +74,8 @@ def load() -> C.CDLL:
     L.cats_field_info.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.cats_workset_field_info.argtypes = L.cats_field_info.argtypes
+    L.cats_field_stride.argtypes = [C.c_char_p]
+    L.cats_field_stride.restype = C.c_int
     L.cats_field_name.restype = C.c_char_p
     L.cats_field_name.argtypes = [C.c_int]
     L.cats_tape_bytes.restype = C.c_size_t
@@ -114,6 +117,14 @@ def field_info(W: int, F: int, N: int, name: str, workset: bool = False):
     fn = load().cats_workset_field_info if workset else load().cats_field_info
     check(fn(W, F, N, name.encode(), C.byref(off), C.byref(cnt), C.byref(dt)))
     return int(off.value), int(cnt.value), int(dt.value)
+
+
+def field_stride(name: str) -> int:
+    """Element stride of a state field (2 for the interleaved household records, else 1)."""
+    st = int(load().cats_field_stride(name.encode()))
+    if st < 1:
+        raise ValueError(f"unknown field '{name}'")
+    return st
 
 
 def field_names() -> list[str]:

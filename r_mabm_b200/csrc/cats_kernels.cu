@@ -81,8 +81,10 @@ struct Ctx {
     __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 32); }
     __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 96); }
     __device__ __forceinline__ int *Oc() const { return reinterpret_cast<int *>(blob + a->L.o_Oc); }          // GLOBAL
-    __device__ __forceinline__ double *PA() const { return reinterpret_cast<double *>(blob + a->L.o_PA); }    // GLOBAL
-    __device__ __forceinline__ double *perm() const { return reinterpret_cast<double *>(blob + a->L.o_perm); }  // GLOBAL
+    // households: {wealth, permanent income} records, GLOBAL
+    __device__ __forceinline__ double2 *hh() const { return reinterpret_cast<double2 *>(blob + a->L.o_PA); }
+    __device__ __forceinline__ double &PA(int h) const { return hh()[h].x; }
+    __device__ __forceinline__ double &perm(int h) const { return hh()[h].y; }
     __device__ __forceinline__ int z_c() const { return (int)par()[P_z_c]; }
     __device__ __forceinline__ int z_k() const { return (int)par()[P_z_k]; }
     __device__ __forceinline__ int z_e() const { return (int)par()[P_z_e]; }
@@ -683,7 +685,7 @@ __device__ void phase_households_only(Ctx &c)
     const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
     const double xi = c.par()[P_xi], chi = c.par()[P_chi];
     for (int h = c.lane; h < L.H; h += 32) {
-        double pa = c.PA()[h], pm = c.perm()[h];
+        double pa = c.PA(h), pm = c.perm(h);
         double inc;
         if (h < L.W) { inc = c.Oc()[h] >= 0 ? wb * (1.0 - c.par()[P_tax_rate]) : sub; pa = pa + inc; }
         else inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
@@ -697,7 +699,7 @@ __device__ void phase_households_only(Ctx &c)
             if (!(b > 0.0)) b = 0.0;
             pa = pa - b;
         }
-        c.PA()[h] = pa; c.perm()[h] = pm;
+        c.PA(h) = pa; c.perm(h) = pm;
     }
     __syncwarp();
 }
@@ -745,7 +747,8 @@ __device__ void phase_goods_market(Ctx &c)
         h_n = -1; oc_n = -1; pa_n = 0.0; pm_n = 0.0; dinc_n = 0.0;
         if (pos < H) {
             const int h = ord.at(pos);
-            h_n = h; pa_n = c.PA()[h]; pm_n = c.perm()[h];
+            const double2 rec = c.hh()[h];
+            h_n = h; pa_n = rec.x; pm_n = rec.y;
             if (h < W) oc_n = c.Oc()[h];
             else if (h < W + F) dinc_n = c.cf(C_div_income)[h - W];
             else dinc_n = c.kf(K_div_income)[h - W - F];
@@ -771,7 +774,7 @@ __device__ void phase_goods_market(Ctx &c)
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
             pa = pa - b;
-            c.perm()[h] = pm;
+            c.perm(h) = pm;
         }
         // a16: candidates, sorted by price, packed 16 bits each
         unsigned long long cp0 = 0ull, cp1 = 0ull;
@@ -852,7 +855,7 @@ __device__ void phase_goods_market(Ctx &c)
             pend &= ~__ballot_sync(FULL, done);
             __syncwarp();
         }
-        if (h >= 0) c.PA()[h] = pa + b;   // involuntary saving
+        if (h >= 0) c.PA(h) = pa + b;   // involuntary saving
     }
     // close: unpack the seller records.  The reductions above were issued by other lanes: fence, then
     // read the accumulators where they live (L2)
@@ -883,7 +886,7 @@ __device__ void phase_accounting(Ctx &c)
         const double Yp = c.cf(C_Y_prev)[f], barYK = c.cf(C_barYK)[f], Kold = c.cf(C_K)[f];
         const double inv_f = c.cf(C_investment)[f], cv = c.cf(C_capital_value)[f], Q_f = c.cf(C_Q)[f];
         const double wages = c.cf(C_wages)[f], interests = c.cf(C_interests)[f], deb = c.cf(C_deb)[f];
-        const double liq0 = c.cf(C_liquidity)[f], A0 = c.cf(C_A)[f], pa_owner = c.PA()[W + f];
+        const double liq0 = c.cf(C_liquidity)[f], A0 = c.cf(C_A)[f], pa_owner = c.PA(W + f);
         c.cf(C_barYK)[f] = delta * barYK + (1.0 - delta) * (Yp / k);
         double dep = (eta * Yp) / k;
         c.cf(C_K)[f] = (Kold - dep) + inv_f;
@@ -902,7 +905,7 @@ __device__ void phase_accounting(Ctx &c)
             liq = liq - dvd; A = A - dvd;
             net = dvd * (1.0 - taxd);
             dt = dvd - net;
-            c.PA()[W + f] = pa_owner + net;
+            c.PA(W + f) = pa_owner + net;
         }
         c.cf(C_div_income)[f] = net;
         c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;
@@ -928,7 +931,7 @@ __device__ void phase_accounting(Ctx &c)
                 liq = liq - dvd; A = A - dvd;
                 net = dvd * (1.0 - taxd);
                 dt = dvd - net;
-                c.PA()[W + F + i] = c.PA()[W + F + i] + net;
+                c.PA(W + F + i) = c.PA(W + F + i) + net;
             }
             c.kf(K_div_income)[i] = net;
             c.kf(K_liquidity)[i] = liq; c.kf(K_A)[i] = A;
@@ -1087,10 +1090,10 @@ __device__ void phase_bankrupt(Ctx &c)
             if (!bad[f]) continue;
             const int ow = W + f;
             double inj = mL > 0.0 ? mL : 0.0;
-            double pa = c.PA()[ow];
+            double pa = c.PA(ow);
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
-            c.PA()[ow] = pa - inj;
+            c.PA(ow) = pa - inj;
             double cv = mK * price_k;
             c.cf(C_liquidity)[f] = inj; c.cf(C_K)[f] = mK; c.cf(C_capital_value)[f] = cv;
             c.cf(C_A)[f] = inj + cv; c.cf(C_deb)[f] = 0.0; c.cf(C_P)[f] = mP;
@@ -1104,10 +1107,10 @@ __device__ void phase_bankrupt(Ctx &c)
             if (!bad[F + i]) continue;
             const int ow = W + F + i;
             double inj = mLk > 0.0 ? mLk : 0.0;
-            double pa = c.PA()[ow];
+            double pa = c.PA(ow);
             if (inj > pa) inj = pa;
             if (!(inj > 0.0)) inj = 0.0;
-            c.PA()[ow] = pa - inj;
+            c.PA(ow) = pa - inj;
             c.kf(K_liquidity)[i] = inj; c.kf(K_A)[i] = inj; c.kf(K_deb)[i] = 0.0;
             c.kf(K_P)[i] = mPk; c.kf(K_Y_prev)[i] = mYk; c.kf(K_Yd)[i] = mYk; c.kf(K_Yavail)[i] = mYk;
             c.kf(K_De)[i] = mYk; c.kf(K_inv)[i] = 0.0; c.kf(K_interest_r)[i] = c.par()[P_r_f];
@@ -1164,7 +1167,7 @@ __device__ void phase_closing(Ctx &c)
     }
     share = __shfl_sync(FULL, share, 0);
     if (share > 0.0)
-        for (int h = L.W + c.lane; h < L.H; h += 32) c.PA()[h] = c.PA()[h] + share;
+        for (int h = L.W + c.lane; h < L.H; h += 32) c.PA(h) = c.PA(h) + share;
     __syncwarp();
 }
 
@@ -1407,8 +1410,8 @@ __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, co
         kf(K_A)[i] = LIQ0; kf(K_liquidity)[i] = LIQ0; kf(K_interest_r)[i] = par[P_r_f];
         kf(K_Yavail)[i] = YK0;
     }
-    double *PA = reinterpret_cast<double *>(blob + L.o_PA), *perm = reinterpret_cast<double *>(blob + L.o_perm);
-    for (int h = tid; h < L.H; h += nt) { PA[h] = PA0; perm[h] = 1.0 / P0; }
+    double2 *hh = reinterpret_cast<double2 *>(blob + L.o_PA);
+    for (int h = tid; h < L.H; h += nt) hh[h] = make_double2(PA0, 1.0 / P0);
     int *Oc = reinterpret_cast<int *>(blob + L.o_Oc);
     for (int w = tid; w < L.W; w += nt) Oc[w] = -1;
 }
@@ -1562,6 +1565,14 @@ int cats_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset
         return CATS_OK;
     }
     return fail(CATS_EINVAL, "unknown field '%s'", name);
+}
+
+int cats_field_stride(const char *name)
+{
+    if (!name) return 0;
+    if (!strcmp(name, "PA") || !strcmp(name, "perm")) return 2;   // {PA, perm} records
+    for (int i = 0; i < kNumFields; ++i) if (!strcmp(name, kFields[i].name)) return 1;
+    return 0;
 }
 
 int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byte_offset, int32_t *count,

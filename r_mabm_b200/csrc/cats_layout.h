@@ -2,7 +2,7 @@
 //
 // One economy = one contiguous blob in HBM (docs/MODEL.md section 2, DESIGN.md "data layout"):
 //
-//   [ scal | hot K-firm rows | Leff |  Oc | C-firm rows | cold K-firm rows | PA | perm ]
+//   [ scal | hot K-firm rows | Leff |  Oc | C-firm rows | cold K-firm rows | {PA, perm} x H ]
 //     `------ resident prefix -----'  `--------------- streamed tail ---------------'
 //
 // One WARP advances one economy.  The resident prefix (aggregates, K-firm tables, head-counts: what
@@ -86,8 +86,9 @@ inline Layout make_layout(int W, int F, int N)
     o = (o + 127) & ~(int64_t)127;
     L.o_c = (int32_t)o; o += (int64_t)NC_FIELDS * L.rowF;
     L.o_kc = (int32_t)o; o += (int64_t)(NK_FIELDS - NK_HOT) * L.rowN;
-    L.o_PA = (int32_t)o; o += up16(8ll * L.H);
-    L.o_perm = (int32_t)o; o += up16(8ll * L.H);
+    // households: one 16-byte record {wealth PA, permanent income perm} each -- the goods market
+    // gathers both for a household visited at random, and a pair is one access and one sector
+    L.o_PA = (int32_t)o; L.o_perm = L.o_PA + 8; o += 16ll * L.H;
     o = (o + 127) & ~(int64_t)127;
     L.blob = (int32_t)o;
     // shared memory

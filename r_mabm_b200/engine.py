@@ -98,8 +98,9 @@ class BatchedCats:
         v = self._views.get(name)
         if v is None:
             off, cnt, dt = nat.field_info(self.W, self.F, self.N, name)
-            v = (self._f64[:, off // 8: off // 8 + cnt] if dt == 0
-                 else self._i32[:, off // 4: off // 4 + cnt])
+            st = nat.field_stride(name)        # 2 for the {PA, perm} household records
+            v = (self._f64[:, off // 8: off // 8 + cnt * st: st] if dt == 0
+                 else self._i32[:, off // 4: off // 4 + cnt * st: st])
             self._views[name] = v
         return v
 

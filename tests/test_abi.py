@@ -33,15 +33,18 @@ def test_layout_queries():
     assert blob % 128 == 0 and 35000 < blob < 45000
     names = nat.field_names()
     assert {"scal", "c_P", "c_Q", "k_P", "c_Leff", "k_Leff", "PA", "perm", "Oc"} <= set(names)
-    spans = []
+    owner = {}   # every byte of the blob belongs to at most one field element
     for n in names:
         off, cnt, dt = nat.field_info(1000, 100, 20, n)
-        size = cnt * (8 if dt == 0 else 4)
-        assert off % (8 if dt == 0 else 4) == 0 and off + size <= blob
-        spans.append((off, off + size, n))
-    spans.sort()
-    for (a0, a1, n0), (b0, b1, n1) in zip(spans, spans[1:]):
-        assert a1 <= b0, f"{n0} overlaps {n1}"
+        esz, st = (8 if dt == 0 else 4), nat.field_stride(n)
+        assert off % esz == 0 and off + ((cnt - 1) * st + 1) * esz <= blob
+        assert st == (2 if n in ("PA", "perm") else 1)          # households are {PA, perm} records
+        for i in range(cnt):
+            for byte in range(off + i * st * esz, off + i * st * esz + esz, 4):
+                assert byte not in owner, f"{n}[{i}] overlaps {owner[byte]}"
+                owner[byte] = n
+    with pytest.raises(ValueError):
+        nat.field_stride("no_such_field")
     assert nat.field_info(1000, 100, 20, "c_P")[1] == 100 and nat.field_info(1000, 100, 20, "PA")[1] == 1120
     with pytest.raises(ValueError):
         nat.field_info(1000, 100, 20, "no_such_field")

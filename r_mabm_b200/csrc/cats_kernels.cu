@@ -77,6 +77,7 @@ struct Ctx {
     __device__ __forceinline__ double *par() const { return reinterpret_cast<double *>(sm + a->L.s_par); }
     __device__ __forceinline__ int *Leff() const { return reinterpret_cast<int *>(sm + a->L.o_Leff); }
     __device__ __forceinline__ int *vac() const { return reinterpret_cast<int *>(sm + a->L.s_vac); }   // Ld == Leff + vac
+    __device__ __forceinline__ unsigned *emp() const { return reinterpret_cast<unsigned *>(sm + a->L.s_emp); }
     __device__ __forceinline__ int *misc() const { return reinterpret_cast<int *>(sm + a->L.s_misc); }
     __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 32); }
     __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 96); }
@@ -412,6 +413,7 @@ __device__ void phase_job_search(Ctx &c)
                 const unsigned bal = __ballot_sync(FULL, un);
                 const int at = U + __popc(bal & c.lt());
                 if (un && at < cap3) byidx[at] = (unsigned short)(base + 32 * q + lane);
+                if (lane == 0 && base + 32 * q < W) c.emp()[(base >> 5) + q] = ~bal;   // employed bits (hires are added below)
                 U += __popc(bal);
             }
         }
@@ -471,6 +473,7 @@ __device__ void phase_job_search(Ctx &c)
             __syncwarp();
             if (has && ((commit >> lane) & 1u)) {
                 c.Oc()[w] = pick;
+                if (listed) atomicOr(&c.emp()[w >> 5], 1u << (w & 31));
                 const unsigned grp = peers & commit;
                 if ((grp & lt) == 0) { int n = __popc(grp); c.vac()[pick] -= n; c.Leff()[pick] += n; }
             }
@@ -478,6 +481,14 @@ __device__ void phase_job_search(Ctx &c)
             __syncwarp();
         }
     }
+    if (!listed) {   // the bits the goods market reads instead of gathering employment links
+        for (int base = 0; base < W; base += 32) {
+            const int w = base + lane;
+            const unsigned bal = __ballot_sync(FULL, w < W && c.Oc()[w] >= 0);
+            if (lane == 0) c.emp()[base >> 5] = bal;
+        }
+    }
+    __syncwarp();
 }
 
 // One consumption-goods seller as the market sees it.  The SoA rows (P, Q, stock) are packed into
@@ -749,7 +760,7 @@ __device__ void phase_goods_market(Ctx &c)
             const int h = ord.at(pos);
             const double2 rec = c.hh()[h];
             h_n = h; pa_n = rec.x; pm_n = rec.y;
-            if (h < W) oc_n = c.Oc()[h];
+            if (h < W) oc_n = ((c.emp()[h >> 5] >> (h & 31)) & 1u) ? 0 : -1;   // employed? (bits set by the job search)
             else if (h < W + F) dinc_n = c.cf(C_div_income)[h - W];
             else dinc_n = c.kf(K_div_income)[h - W - F];
         }

@@ -65,6 +65,7 @@ struct Layout {
     int32_t s_ic;                   // int32 x (F+N): firing buckets (count | cursor << 16) / capital-market buyers
     int32_t s_bad;                  // uint8 x (F+N): bankrupt flags
     int32_t s_U, U_bytes;           // union: goods-market seller records | firing pool | job seekers
+    int32_t s_emp;                  // uint32 x ceil(W/32): employed bit per worker (job search -> goods market)
     int32_t s_par, s_misc, smem;
     // debug image (cats_workset_*): transients dumped after a stop_phase step
     int32_t d_Ld, d_vac, d_cFtot, d_cKdem, d_cYstock, d_cvalinv, d_kFtot, d_kYstock, workset;
@@ -106,6 +107,7 @@ inline Layout make_layout(int W, int F, int N)
     int64_t u = 28ll * F;   // seller table: (stock, 1/price) 16 B + price 8 B + class 4 B
     if (2ll * W > u) u = 2ll * W;
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
+    L.s_emp = (int32_t)o; o += up16(4ll * ((W + 31) / 32));
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;
     L.s_misc = (int32_t)o; o += 176;   // status | mbarrier | OrderKeys | goods-market constants (9 x f64)
     L.smem = (int32_t)o;

@@ -154,7 +154,7 @@ uint64_t cats_launch_count(void);
  * 10 bankruptcy, 11 closing).  Pass NULL to switch it off. */
 void cats_debug_phase_cycles(void *d_cycles16);
 
-/* Debug aid: economies per thread block for later cats_step calls (1, 2, 4, 8 or 12; 0 = chosen per
+/* Debug aid: economies per thread block for later cats_step calls (1, 2, 4, 8, 12 or 14; 0 = chosen per
  * launch from batch size and working set, the default).  Results never depend on it: the warps of a
  * block share nothing but their start time; tests/ run every shape. */
 void cats_debug_set_group(int economies_per_block);

@@ -79,8 +79,8 @@ struct Ctx {
     __device__ __forceinline__ int *vac() const { return reinterpret_cast<int *>(sm + a->L.s_vac); }   // Ld == Leff + vac
     __device__ __forceinline__ unsigned *emp() const { return reinterpret_cast<unsigned *>(sm + a->L.s_emp); }
     __device__ __forceinline__ int *misc() const { return reinterpret_cast<int *>(sm + a->L.s_misc); }
-    __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 32); }
-    __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 96); }
+    __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 16); }
+    __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 56); }
     __device__ __forceinline__ int *Oc() const { return reinterpret_cast<int *>(blob + a->L.o_Oc); }          // GLOBAL
     // households: {wealth, permanent income} records, GLOBAL
     __device__ __forceinline__ double2 *hh() const { return reinterpret_cast<double2 *>(blob + a->L.o_PA); }
@@ -1270,7 +1270,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     c.sm = smem; c.a = &a;
     c.lane = threadIdx.x & 31;
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 8);
     const long long b = (long long)blockIdx.x * G + (threadIdx.x >> 5);
     if (b >= a.B) {
         if (G > 1) for (int t = 0; t < a.n_periods; ++t) {   // keep the block's barrier count
@@ -1438,10 +1438,9 @@ static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 static int g_group = 0;                // debug: set by cats_debug_set_group() (0 = automatic)
 constexpr int kThreads = 32;    // one warp per economy
-#ifndef CATS_MIN_BLOCKS
-#define CATS_MIN_BLOCKS 24
-#endif
-constexpr int kMinBlocks = CATS_MIN_BLOCKS;   // __launch_bounds__ hint: register budget for this many resident economies / SM
+// economies resident per SM that the register budget is cut for (__launch_bounds__): 28 x 32 threads
+// x 72 registers fill the register file; shared memory (8.2 KB per default-size economy) allows the same
+constexpr int kMaxPerSM = 28;
 typedef void (*KernelFn)(const KArgs);
 // development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
 static int smem_pad()
@@ -1454,13 +1453,12 @@ template <int ZM>
 static KernelFn select_group(int g)
 {
     switch (g) {
-    case 2: return cats_period_kernel<ZM, 2, kMinBlocks / 2>;
-    case 4: return cats_period_kernel<ZM, 4, kMinBlocks / 4>;
-    case 8: return cats_period_kernel<ZM, 8, kMinBlocks / 8>;
-    case 12: return cats_period_kernel<ZM, 12, kMinBlocks / 12>;
-
-
-    default: return cats_period_kernel<ZM, 1, kMinBlocks>;
+    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2>;
+    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4>;
+    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8>;
+    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12>;
+    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14>;
+    default: return cats_period_kernel<ZM, 1, kMaxPerSM>;
     }
 }
 static KernelFn select_kernel(int max_z, int g)
@@ -1468,12 +1466,12 @@ static KernelFn select_kernel(int max_z, int g)
     if (max_z > 0 && max_z <= 5) return select_group<5>(g);
     return select_group<MAX_Z>(g);
 }
-static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 127) & ~127; }
+static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 15) & ~15; }
 // Economies per block (see cats_period_kernel).  Shared memory and the register file bound how many
-// economies fit on an SM (at most kMinBlocks).  The launch takes as long as its busiest SM; a period
+// economies fit on an SM (at most kMaxPerSM).  The launch takes as long as its busiest SM; a period
 // on an SM with n resident economies costs about (12 + n) units (measured: latency + contention), and
 // economies that run in step save instruction fetches (measured factors below).  The cheapest shape
-// wins.  CATS_GROUP=<1|2|4|8|12> overrides (development aid).
+// wins.  CATS_GROUP=<1|2|4|8|12|14> overrides (development aid).
 static int choose_group(const Layout &L, long long B, int sms)
 {
     static int env_forced = -1;
@@ -1481,21 +1479,21 @@ static int choose_group(const Layout &L, long long B, int sms)
     const int forced = g_group ? g_group : env_forced;
     const int slice = slice_bytes(L);
     const int sm_bytes = 228 * 1024, block_max = 227 * 1024, reserve = 1024;
-    const int cand[5] = {12, 8, 4, 2, 1};
+    const int cand[6] = {14, 12, 8, 4, 2, 1};
     if (sms < 1) sms = 1;
     int best = 1; double best_score = 1e300;
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 6; ++i) {
         const int g = cand[i];
         if (g > 1 && g * slice > block_max) continue;
         if (forced == g) return g;
         long long fit = sm_bytes / (g * (long long)slice + reserve);     // blocks resident per SM
-        if (fit > kMinBlocks / g) fit = kMinBlocks / g;
+        if (fit > kMaxPerSM / g) fit = kMaxPerSM / g;
         if (fit < 1) fit = 1;
         const long long blocks = (B + g - 1) / g;
         long long per_sm = (blocks + sms - 1) / sms;                     // blocks on the busiest SM ...
-        const double waves = (double)per_sm / (double)fit;               // ... in this many rounds of `fit`
+        const double waves = (double)((per_sm + fit - 1) / fit);         // ... in this many rounds of `fit`
         if (per_sm > fit) per_sm = fit;
-        const double step[5] = {0.62, 0.68, 0.75, 0.85, 1.0};             // g = 12, 8, 4, 2, 1
+        const double step[6] = {0.60, 0.62, 0.68, 0.75, 0.85, 1.0};       // g = 14, 12, 8, 4, 2, 1
         const double score = (waves > 1.0 ? waves : 1.0) * (12.0 + (double)(per_sm * g)) * step[i];
         if (score < best_score) { best_score = score; best = g; }
     }

@@ -109,7 +109,7 @@ inline Layout make_layout(int W, int F, int N)
     L.s_U = (int32_t)o; L.U_bytes = up16(u); o += L.U_bytes;
     L.s_emp = (int32_t)o; o += up16(4ll * ((W + 31) / 32));
     L.s_par = (int32_t)o; o += 8 * P_SLOTS;
-    L.s_misc = (int32_t)o; o += 176;   // status | mbarrier | OrderKeys | goods-market constants (9 x f64)
+    L.s_misc = (int32_t)o; o += 128;   // status 8 B | mbarrier 8 B | OrderKeys 40 B | goods-market constants 9 x f64
     L.smem = (int32_t)o;
     // debug image
     o = 0;

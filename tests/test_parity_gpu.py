@@ -80,14 +80,14 @@ def test_batch_size_and_sharding_invariance():
 
 
 def test_block_shape_never_changes_results():
-    """Economies per block is a scheduling choice: 1, 2, 4, 8 and 12 per block, with
+    """Economies per block is a scheduling choice: 1, 2, 4, 8, 12 and 14 per block, with
     a ragged last block and with the per-period barriers of a multi-period launch, give the same bits."""
     from r_mabm_b200 import _native as nat
     from r_mabm_b200.engine import BatchedCats
     lib = nat.load()
     ref = None
     try:
-        for g in (1, 2, 4, 8, 12, 0):
+        for g in (1, 2, 4, 8, 12, 14, 0):
             lib.cats_debug_set_group(g)
             env = BatchedCats(29, W=200, F=20, N=5, n_agents=1, seed=11)
             env.run(7)

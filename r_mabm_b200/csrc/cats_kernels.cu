@@ -804,21 +804,23 @@ __device__ void phase_goods_market(Ctx &c)
                 else cp1 |= (unsigned long long)(key[k] & 0x3fffu) << (16 * (k - 4));
             }
         }
-        int nrem = b > 0.0 ? z : 0, term = -1;
+        // term: the seller this lane will buy from (>= 0), TERM_NONE (nothing left to visit / done)
+        // or TERM_WALK (has budget and must walk down its list to the next seller with stock)
+        enum { TERM_NONE = -1, TERM_WALK = -2 };
+        int nrem = b > 0.0 ? z : 0, term = b > 0.0 ? TERM_WALK : TERM_NONE;
         double d_t = 0.0;
-        bool dirty = b > 0.0;
         unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
         while (pend) {
             // ---- walk: dirty lanes register demand seller by seller until one has stock
-            while (__any_sync(FULL, dirty)) {
-                if (dirty) {
-                    if (nrem == 0) { term = -1; dirty = false; }   // every candidate is sold out
+            while (__any_sync(FULL, term == TERM_WALK)) {
+                if (term == TERM_WALK) {
+                    if (nrem == 0) term = TERM_NONE;   // every candidate is sold out
                     else {
                         const int cnd = (int)(cp0 & 0xffffull);
                         cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
                         const double2 yr = mkt.yr[cnd];   // stock, 1 / price
                         fx_red(&acc[cnd], xb);
-                        if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; dirty = false; }
+                        if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
                     }
                 }
             }
@@ -853,15 +855,14 @@ __device__ void phase_goods_market(Ctx &c)
                     if (full) { ys = ys - d_t; b = 0.0; done = true; }
                     else {                                 // lane s: partial fill, then walk on
                         b = b - ys * mkt.p[seller]; ys = 0.0;
-                        term = -1;
-                        dirty = b > 0.0;
-                        done = !dirty;
+                        term = b > 0.0 ? TERM_WALK : TERM_NONE;
+                        done = term == TERM_NONE;
                         xb = fx_from(b * rpavg);
                     }
                     if (lastp) mkt.yr[seller].x = ys;
                 }
             } else if (mine && so && has && term == xs) {
-                term = -1; dirty = true;                   // queued behind lane s at the exhausted seller
+                term = TERM_WALK;                          // queued behind lane s at the exhausted seller
             }
             pend &= ~__ballot_sync(FULL, done);
             __syncwarp();

@@ -812,7 +812,9 @@ __device__ void phase_goods_market(Ctx &c)
         unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
         while (pend) {
             // ---- walk: dirty lanes register demand seller by seller until one has stock
-            while (__any_sync(FULL, term == TERM_WALK)) {
+            // (a round nearly always has a walker -- the chunk's first round, or the lane that just
+            // exhausted a seller -- so the test comes after the step)
+            do {
                 if (term == TERM_WALK) {
                     if (nrem == 0) term = TERM_NONE;   // every candidate is sold out
                     else {
@@ -823,7 +825,7 @@ __device__ void phase_goods_market(Ctx &c)
                         if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
                     }
                 }
-            }
+            } while (__any_sync(FULL, term == TERM_WALK));
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
             const bool mine = (pend >> lane) & 1u;
             const bool has = mine && term >= 0;

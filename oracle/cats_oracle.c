@@ -13,6 +13,12 @@
  * field protocol visible at cats.py:355-410 and cats.py:434-626.  Every rule is written down in
  * docs/MODEL.md; this file and the CUDA kernels are two independent implementations of that spec.
  *
+ * PINNED against the reference itself: the part of the path the reference implements in Python --
+ * the call order of Cats.step, the action override, reward, termination, observations (ph_action,
+ * ph_reward, oracle_obs, oracle_step below).  tests/golden/make_reference_driver.py runs the unmodified
+ * /root/reference/rmabm code over a juliacall stand-in that forwards each ABCredit call to the ph_*
+ * function here; tests/test_reference_driver.py holds oracle_step against what the reference returned.
+ *
  * Plain C99, one economy at a time, deliberately simple.  Compile with
  *   gcc -O2 -std=c99 -ffp-contract=off -fPIC -shared (see oracle/Makefile)
  * -ffp-contract=off matters: the spec's arithmetic is "every * and + rounds separately".

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CATS_ABI_VERSION 1
+#define CATS_ABI_VERSION 2
 #define CATS_N_PARAMS 34   /* Cats._default_parameters, cats.py:69-104, in that key order */
 #define CATS_N_SCAL 32
 #define CATS_N_STATS 16
@@ -90,6 +90,16 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
 int cats_init(void *d_blobs, int64_t B, int W, int F, int N, const double *d_params,
               int64_t params_stride, void *stream);
 
+/* Per-economy reset, for episodes that end at different times (a new model per `Cats.reset`,
+ * cats.py:283-315, one economy at a time): re-initialises the economies whose d_active[b] != 0 and
+ * leaves the others untouched.  A reset economy's EPISODE counter (scal slot "episode") goes up by
+ * one; it is part of the Philox counter (docs/MODEL.md 3.1), so the new episode draws a fresh stream
+ * while staying a pure function of (seed, global economy id, episode, period).  cats_init() puts
+ * the counter back to zero.  Follow with cats_step(n_periods = t_burnin, BURNIN flag, the same
+ * d_active) for the burn-in of the reset economies only. */
+int cats_reset_masked(void *d_blobs, int64_t B, int W, int F, int N, const double *d_params,
+                      int64_t params_stride, const uint8_t *d_active, void *stream);
+
 typedef struct cats_step_args {
     void *d_blobs;              /* [B] economy blobs */
     int64_t B;
@@ -116,6 +126,8 @@ typedef struct cats_step_args {
     int32_t stop_phase;         /* debug: halt the (single) period after this phase id; 0 = off */
     void *d_debug;              /* debug: [B][cats_workset_bytes] image of the on-chip working set */
     void *stream;
+    const uint8_t *d_active;    /* DEVICE [B] or NULL: economies with a zero entry sit this call out (state
+                                   and outputs untouched); NULL = all.  See cats_reset_masked(). */
 } cats_step_args;
 
 /* Replaces the 26 ABCredit calls of one Cats.step (cats.py:355-413) plus _implement_action,

@@ -44,7 +44,7 @@ enum {
     S_gdp_deflator, S_inflationRate, S_Un, S_consumption, S_totK, S_bankruptcy_rate,
     S_bank_E, S_bank_loans, S_profitsB, S_dividendsB, S_bank_interest_income, S_bank_bad_debt,
     S_gov_bonds, S_GB, S_deficitGDP, S_gov_TA, S_gov_G, S_gov_r_b, S_gov_subsidy_level,
-    S_terminated, S_status, S_reserved0, S_reserved1, S_reserved2, N_SCAL
+    S_terminated, S_status, S_episode, S_reserved1, S_reserved2, N_SCAL
 };
 
 /* C-firm fp64 fields, K-firm fp64 fields (persisted) */
@@ -184,8 +184,8 @@ static double det_sum(const double *x, int n)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Philox-4x32-10 (Salmon et al. 2011), counter = (agent, phase<<8|block, period, economy),     */
-/* key = (seed_lo, seed_hi)                                                                    */
+/* Philox-4x32-10 (Salmon et al. 2011), counter = (agent, phase<<8|block, episode<<20|period,   */
+/* economy), key = (seed_lo, seed_hi)                                                          */
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                           uint32_t k1, uint32_t out[4])
 {
@@ -205,7 +205,7 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 static void econ_philox(const Econ *e, uint32_t agent, uint32_t phase, uint32_t block,
                         uint32_t out[4])
 {
-    uint32_t period = (uint32_t)e->scal[S_timestep];
+    uint32_t period = (uint32_t)e->scal[S_timestep] + ((uint32_t)e->scal[S_episode] << 20);
     philox4x32_10(agent, (phase << 8) | block, period, e->economy, (uint32_t)e->seed,
                   (uint32_t)(e->seed >> 32), out);
 }
@@ -381,6 +381,30 @@ static int order_at(const Order *o, int pos)
 /* a0: initialise_model (cats.py:224).  Deterministic: no draws.  docs/MODEL.md section 5.      */
 static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
 
+/* a0 initialise_model (cats.py:224): the deterministic initial state, docs/MODEL.md section 5 */
+static void init_state(Econ *e)
+{
+    int W = e->W, F = e->F, N = e->N;
+    const double P0 = 3.0, PK0 = 3.0, K0 = 10.0, LIQ0 = 10.0, YC0 = 5.0, YK0 = 3.0, PA0 = 2.0;
+    double *s = e->scal;
+    s[S_timestep] = 0.0; s[S_price] = P0; s[S_price_k] = PK0; s[S_init_price] = P0;
+    s[S_init_price_k] = PK0; s[S_wb] = e->par[P_wb]; s[S_bank_E] = 3000.0;
+    s[S_gdp_deflator] = 1.0; s[S_Un] = 1.0; s[S_gov_r_b] = e->par[P_interest_rate];
+    for (int f = 0; f < F; ++f) {
+        e->c[C_De][f] = 1.0; e->c[C_P][f] = P0; e->c[C_Y_prev][f] = YC0; e->c[C_Yd][f] = YC0;
+        e->c[C_K][f] = K0; e->c[C_capital_value][f] = K0 * PK0; e->c[C_liquidity][f] = LIQ0;
+        e->c[C_A][f] = LIQ0 + K0 * PK0; e->c[C_barYK][f] = YC0 / e->par[P_k];
+        e->c[C_interest_r][f] = e->par[P_r_f];
+    }
+    for (int i = 0; i < N; ++i) {
+        e->k[K_De][i] = 1.0; e->k[K_P][i] = PK0; e->k[K_Y_prev][i] = YK0; e->k[K_Yd][i] = YK0;
+        e->k[K_A][i] = LIQ0; e->k[K_liquidity][i] = LIQ0; e->k[K_interest_r][i] = e->par[P_r_f];
+        e->k[K_Yavail][i] = YK0;
+    }
+    for (int h = 0; h < e->H; ++h) { e->PA[h] = PA0; e->perm[h] = 1.0 / P0; }
+    for (int w = 0; w < W; ++w) e->Oc[w] = -1;
+}
+
 Econ *oracle_create(int W, int F, int N, const double *params34, uint64_t seed, uint32_t economy)
 {
     Econ *e = (Econ *)xcalloc(1, sizeof(Econ));
@@ -401,26 +425,25 @@ Econ *oracle_create(int W, int F, int N, const double *params34, uint64_t seed, 
     e->k_Ftot = (double *)xcalloc((size_t)N, 8); e->k_Ystock = (double *)xcalloc((size_t)N, 8);
     e->income = (double *)xcalloc((size_t)W, 8); e->budget = (double *)xcalloc((size_t)e->H, 8);
 
-    const double P0 = 3.0, PK0 = 3.0, K0 = 10.0, LIQ0 = 10.0, YC0 = 5.0, YK0 = 3.0, PA0 = 2.0;
-    double *s = e->scal;
-    s[S_timestep] = 0.0; s[S_price] = P0; s[S_price_k] = PK0; s[S_init_price] = P0;
-    s[S_init_price_k] = PK0; s[S_wb] = e->par[P_wb]; s[S_bank_E] = 3000.0;
-    s[S_gdp_deflator] = 1.0; s[S_Un] = 1.0; s[S_gov_r_b] = e->par[P_interest_rate];
-    for (int f = 0; f < F; ++f) {
-        e->c[C_De][f] = 1.0; e->c[C_P][f] = P0; e->c[C_Y_prev][f] = YC0; e->c[C_Yd][f] = YC0;
-        e->c[C_K][f] = K0; e->c[C_capital_value][f] = K0 * PK0; e->c[C_liquidity][f] = LIQ0;
-        e->c[C_A][f] = LIQ0 + K0 * PK0; e->c[C_barYK][f] = YC0 / e->par[P_k];
-        e->c[C_interest_r][f] = e->par[P_r_f];
-    }
-    for (int i = 0; i < N; ++i) {
-        e->k[K_De][i] = 1.0; e->k[K_P][i] = PK0; e->k[K_Y_prev][i] = YK0; e->k[K_Yd][i] = YK0;
-        e->k[K_A][i] = LIQ0; e->k[K_liquidity][i] = LIQ0; e->k[K_interest_r][i] = e->par[P_r_f];
-        e->k[K_Yavail][i] = YK0;
-    }
-    for (int h = 0; h < e->H; ++h) { e->PA[h] = PA0; e->perm[h] = 1.0 / P0; }
-    for (int w = 0; w < W; ++w) e->Oc[w] = -1;
+    init_state(e);
     e->bankruptcy_reward = -100.0;
     return e;
+}
+
+/* Per-economy reset (cats_reset_masked): a new model in place, episode counter + 1 (the salt of
+ * the economy's Philox stream, see econ_philox). */
+void oracle_reset(Econ *e)
+{
+    double episode = e->scal[S_episode] + 1.0;
+    int F = e->F, N = e->N, W = e->W, H = e->H;
+    memset(e->scal, 0, sizeof e->scal);
+    for (int i = 0; i < NC_FIELDS; ++i) memset(e->c[i], 0, 8u * (size_t)F);
+    for (int i = 0; i < NK_FIELDS; ++i) memset(e->k[i], 0, 8u * (size_t)N);
+    memset(e->c_Leff, 0, 4u * (size_t)F); memset(e->k_Leff, 0, 4u * (size_t)N);
+    memset(e->PA, 0, 8u * (size_t)H); memset(e->perm, 0, 8u * (size_t)H);
+    memset(e->Oc, 0, 4u * (size_t)W);
+    init_state(e);
+    e->scal[S_episode] = episode;
 }
 
 void oracle_destroy(Econ *e)

@@ -35,7 +35,7 @@ SCAL_NAMES = [
     "gdp_deflator", "inflationRate", "Un", "consumption", "totK", "bankruptcy_rate", "bank_E",
     "bank_loans", "profitsB", "dividendsB", "bank_interest_income", "bank_bad_debt", "gov_bonds",
     "GB", "deficitGDP", "gov_TA", "gov_G", "gov_r_b", "gov_subsidy_level", "terminated", "status",
-    "reserved0", "reserved1", "reserved2",
+    "episode", "reserved1", "reserved2",
 ]
 C_FIELDS = ["De", "P", "Y_prev", "Yd", "Q", "A", "K", "investment", "capital_value", "wages",
             "interests", "deb", "liquidity", "barYK", "interest_r", "div_income"]
@@ -160,6 +160,10 @@ class OracleEconomy:
         rec = np.zeros(self.tape_bytes(), dtype=np.uint8)
         self._L.oracle_fill_tape(self._h, rec.ctypes.data)
         return rec
+
+    def reset(self) -> None:
+        """A new model in place, episode counter + 1 (cats_reset_masked)."""
+        self._L.oracle_reset(self._h)
 
     def set_stop_phase(self, p: int) -> None:
         self._L.oracle_set_stop_phase(self._h, p)

@@ -31,10 +31,13 @@ STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_t
 EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
     "cats_field_stride",
-    "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_step", "cats_host_scratch_bytes",
+    "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_reset_masked", "cats_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
     "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group",
 ]
+
+
+ABI_VERSION = 2
 
 
 class StepArgs(C.Structure):
@@ -48,6 +51,7 @@ class StepArgs(C.Structure):
         ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p), ("d_status", C.c_void_p),
         ("d_stats", C.c_void_p), ("d_tape", C.c_void_p), ("tape_z", C.c_int32 * 3),
         ("max_z", C.c_int32), ("stop_phase", C.c_int32), ("d_debug", C.c_void_p), ("stream", C.c_void_p),
+        ("d_active", C.c_void_p),
     ]
 
 
@@ -83,6 +87,8 @@ def load() -> C.CDLL:
     L.cats_tape_offsets.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_uint64)]
     L.cats_init.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
                             C.c_void_p]
+    L.cats_reset_masked.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p]
     L.cats_step.argtypes = [C.POINTER(StepArgs)]
     L.cats_host_scratch_bytes.restype = C.c_size_t
     L.cats_host_scratch_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
@@ -93,8 +99,8 @@ def load() -> C.CDLL:
     L.cats_debug_phase_cycles.restype = None
     L.cats_debug_set_group.argtypes = [C.c_int]
     L.cats_debug_set_group.restype = None
-    if L.cats_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {L.cats_abi_version()} != 1; rebuild")
+    if L.cats_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.cats_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = L
     return L
 

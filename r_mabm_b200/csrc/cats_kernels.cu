@@ -60,6 +60,7 @@ struct KArgs {
     long long *cycles;  // debug: [16] per-phase clock64 totals of block 0
     int slice;          // bytes of shared memory per economy (Layout::smem rounded up to 128)
     int bars;           // 1: the block re-aligns before the accounting phases (0 under stop_phase)
+    const unsigned char *active;  // [B] or nullptr: economies with a zero entry sit this launch out
 };
 
 // per-warp view of the working set.  Only two base pointers are kept: every section address is
@@ -100,7 +101,7 @@ struct Ctx {
     __device__ __forceinline__ int *iat(int off) const { return reinterpret_cast<int *>(sm + off); }
 };
 
-enum { M_STATUS = 0 };
+enum { M_STATUS = 0, M_EPISODE = 1 };   // M_EPISODE: the economy's episode counter << 20 (Philox counter word 2)
 constexpr int JOB_SORT_MAX = 128;   // job search: up to this many seekers are sorted by position (see phase_job_search)
 
 __device__ __forceinline__ double bfly(double a)
@@ -1263,7 +1264,10 @@ __device__ void run_period(Ctx &c)
 // that run in step fetch each instruction line once for all of them.  One-warp blocks are rescheduled
 // one by one and spread over all phases, which costs a quarter of the throughput in instruction-cache
 // misses ("instruction supply").  Multi-period launches re-align at every period.
-template <int ZM, int G, int MINB>
+// MASKED: the launch honours KArgs::active (per-economy resets).  A separate instantiation, so that
+// the test at the kernel entry cannot disturb the register allocation of the common, unmasked path
+// (measured: the same source with the test compiled in is 3 % slower even when active == nullptr).
+template <int ZM, int G, int MINB, bool MASKED>
 __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_block[];
@@ -1275,7 +1279,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 8);
     const long long b = (long long)blockIdx.x * G + (threadIdx.x >> 5);
-    if (b >= a.B) {
+    if (b >= a.B || (MASKED && !a.active[b])) {
         if (G > 1) for (int t = 0; t < a.n_periods; ++t) {   // keep the block's barrier count
             if (t > 0) __syncthreads();
             if (a.bars) __syncthreads();
@@ -1306,6 +1310,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
         for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
     __syncwarp();
     mbar_wait(bar, 0);
+    if (c.lane == 0) c.misc()[M_EPISODE] = (int)((uint32_t)c.scal()[S_episode] << 20);
     __syncwarp();
 
     c.d.k0 = a.k0; c.d.k1 = a.k1;
@@ -1315,7 +1320,8 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
 
     for (int t = 0; t < a.n_periods; ++t) {
         if (G > 1 && t > 0) __syncthreads();   // back in step (see above)
-        c.d.period = (uint32_t)c.scal()[S_timestep];
+        // counter word 2: period in the low 20 bits, episode (bumped by a masked reset) above them
+        c.d.period = (uint32_t)c.scal()[S_timestep] + (uint32_t)c.misc()[M_EPISODE];
         c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
         run_period<ZM, G>(c);
         __syncwarp();
@@ -1395,12 +1401,16 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
 }
 
 // a0: initialise_model (cats.py:224) -- deterministic initial state, docs/MODEL.md section 5
+// `active` (nullable): only economies with a non-zero entry are re-initialised, and their episode
+// counter -- the salt of their Philox stream -- goes up by one instead of back to zero.
 __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, const double *params,
-                                 long long params_stride)
+                                 long long params_stride, const unsigned char *active)
 {
     const long long b = blockIdx.x;
-    if (b >= B) return;
+    if (b >= B || (active && !active[b])) return;
     unsigned char *blob = blobs + (size_t)b * (size_t)L.blob;
+    const double episode = active ? reinterpret_cast<const double *>(blob + L.o_scal)[S_episode] + 1.0 : 0.0;
+    __syncthreads();
     const double *par = params + (params_stride ? (size_t)b * (size_t)params_stride : 0);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < L.blob / 8; i += nt) reinterpret_cast<double *>(blob)[i] = 0.0;
@@ -1411,6 +1421,7 @@ __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, co
         scal[S_price] = P0; scal[S_price_k] = PK0; scal[S_init_price] = P0; scal[S_init_price_k] = PK0;
         scal[S_wb] = par[P_wb]; scal[S_bank_E] = 3000.0; scal[S_gdp_deflator] = 1.0; scal[S_Un] = 1.0;
         scal[S_gov_r_b] = par[P_interest_rate];
+        scal[S_episode] = episode;
     }
     auto cf = [&](int f) { return reinterpret_cast<double *>(blob + L.o_c + f * L.rowF); };
     auto kf = [&](int f) { return reinterpret_cast<double *>(blob + (f < NK_HOT ? L.o_kh + f * L.rowN : L.o_kc + (f - NK_HOT) * L.rowN)); };
@@ -1452,22 +1463,23 @@ static int smem_pad()
     if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
     return pad;
 }
-template <int ZM>
+template <int ZM, bool MASKED>
 static KernelFn select_group(int g)
 {
     switch (g) {
-    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2>;
-    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4>;
-    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8>;
-    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12>;
-    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14>;
-    default: return cats_period_kernel<ZM, 1, kMaxPerSM>;
+    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2, MASKED>;
+    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4, MASKED>;
+    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8, MASKED>;
+    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12, MASKED>;
+    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14, MASKED>;
+    default: return cats_period_kernel<ZM, 1, kMaxPerSM, MASKED>;
     }
 }
-static KernelFn select_kernel(int max_z, int g)
+static KernelFn select_kernel(int max_z, int g, bool masked = false)
 {
-    if (max_z > 0 && max_z <= 5) return select_group<5>(g);
-    return select_group<MAX_Z>(g);
+    if (masked) return select_group<MAX_Z, true>(g);   // resets are rare: one instantiation serves every z
+    if (max_z > 0 && max_z <= 5) return select_group<5, false>(g);
+    return select_group<MAX_Z, false>(g);
 }
 static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 15) & ~15; }
 // Economies per block (see cats_period_kernel).  Shared memory and the register file bound how many
@@ -1672,10 +1684,26 @@ int cats_init(void *d_blobs, int64_t B, int W, int F, int N, const double *d_par
     if (B == 0) return CATS_OK;
     Layout L = make_layout(W, F, N);
     cats_init_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((unsigned char *)d_blobs, B, L, d_params,
-                                                                   params_stride);
+                                                                   params_stride, nullptr);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_init launch: %s", cudaGetErrorString(e));
+    return CATS_OK;
+}
+
+int cats_reset_masked(void *d_blobs, int64_t B, int W, int F, int N, const double *d_params,
+                      int64_t params_stride, const uint8_t *d_active, void *stream)
+{
+    if (int rc = check_sizes(W, F, N)) return rc;
+    if (!d_blobs || !d_params || !d_active || B < 0) return fail(CATS_EINVAL, "cats_reset_masked: null pointer or negative B%s", "");
+    if (params_stride != 0 && params_stride < CATS_N_PARAMS) return fail(CATS_EINVAL, "params_stride must be 0 or >= 34%s", "");
+    if (B == 0) return CATS_OK;
+    Layout L = make_layout(W, F, N);
+    cats_init_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((unsigned char *)d_blobs, B, L, d_params,
+                                                                   params_stride, d_active);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_reset_masked launch: %s", cudaGetErrorString(e));
     return CATS_OK;
 }
 
@@ -1711,6 +1739,7 @@ int cats_step(const cats_step_args *s)
     a.stats = s->d_stats; a.tape = s->d_tape; a.stop_phase = s->stop_phase;
     a.debug = (unsigned char *)s->d_debug;
     a.cycles = g_cycles;
+    a.active = s->d_active;
     if (s->d_tape) {
         a.T = make_tape(s->W, s->F, s->N, s->tape_z[0], s->tape_z[1], s->tape_z[2]);
         a.tape_z[0] = s->tape_z[0]; a.tape_z[1] = s->tape_z[1]; a.tape_z[2] = s->tape_z[2];
@@ -1721,7 +1750,7 @@ int cats_step(const cats_step_args *s)
     const int g = choose_group(a.L, s->B, nsm);
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
-    KernelFn fn = select_kernel(s->max_z, g);
+    KernelFn fn = select_kernel(s->max_z, g, s->d_active != nullptr);
     if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
     fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
     g_launches++;

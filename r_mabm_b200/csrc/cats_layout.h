@@ -42,7 +42,7 @@ enum {
     S_gdp_deflator, S_inflationRate, S_Un, S_consumption, S_totK, S_bankruptcy_rate,
     S_bank_E, S_bank_loans, S_profitsB, S_dividendsB, S_bank_interest_income, S_bank_bad_debt,
     S_gov_bonds, S_GB, S_deficitGDP, S_gov_TA, S_gov_G, S_gov_r_b, S_gov_subsidy_level,
-    S_terminated, S_status, S_reserved0, S_reserved1, S_reserved2
+    S_terminated, S_status, S_episode, S_reserved1, S_reserved2
 };
 
 // C-firm / K-firm float64 rows

@@ -136,8 +136,30 @@ class BatchedCats:
                                           self._stream()))
         self.periods_done = 0
 
+    def _active(self, active: torch.Tensor | None) -> torch.Tensor | None:
+        if active is None:
+            return None
+        if tuple(active.shape) != (self.B,) or not active.is_cuda:
+            raise ValueError(f"active must be a CUDA tensor of shape ({self.B},)")
+        return active.to(torch.uint8).contiguous() if active.dtype != torch.uint8 else active.contiguous()
+
+    def reset_where(self, active: torch.Tensor, t_burnin: int = 0) -> None:
+        """Per-economy `Cats.reset` (cats.py:283-315) without leaving the device: the economies whose
+        `active[b]` is set get a new model and `t_burnin` heuristic periods; the others are not
+        touched.  A reset economy's episode counter goes up by one and salts its Philox stream, so the
+        new episode is a fresh draw that still depends only on (seed, economy id, episode, period).
+        `active` is a bool / uint8 CUDA tensor [B] -- e.g. `terminated | truncated` -- and is never
+        read on the host: no synchronisation, two launches."""
+        act = self._active(active)
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.cats_reset_masked(self._blob.data_ptr(), self.B, self.W, self.F, self.N,
+                                                  self._params_t.data_ptr(), self._params_stride,
+                                                  act.data_ptr(), self._stream()))
+        if t_burnin > 0:
+            self.run(t_burnin, active=act)
+
     def _args(self, n_periods: int, flags: int, actions=None, mask=None, stats=None, tape=None,
-              stop_phase: int = 0, debug=None, want_io: bool = True) -> nat.StepArgs:
+              stop_phase: int = 0, debug=None, want_io: bool = True, active=None) -> nat.StepArgs:
         a = nat.StepArgs()
         a.d_blobs = self._blob.data_ptr(); a.B = self.B
         a.W, a.F, a.N = self.W, self.F, self.N
@@ -160,29 +182,35 @@ class BatchedCats:
         a.stop_phase = stop_phase
         a.d_debug = debug.data_ptr() if debug is not None else None
         a.stream = self._stream()
+        a.d_active = active.data_ptr() if active is not None else None
         return a
 
-    def run(self, n_periods: int, want_stats: bool = False, tape: torch.Tensor | None = None):
+    def run(self, n_periods: int, want_stats: bool = False, tape: torch.Tensor | None = None,
+            active: torch.Tensor | None = None):
         """Advance every economy `n_periods` heuristic periods in ONE launch (state stays on chip
         between periods).  This is the burn-in of `Cats.reset` (cats.py:423-432) and the
-        Monte-Carlo path.  Returns [B, n_periods, 16] statistics if asked."""
+        Monte-Carlo path.  Returns [B, n_periods, 16] statistics if asked.  `active` ([B] bool/uint8
+        CUDA tensor): only those economies advance (rows of the others in the statistics are zero)."""
         stats = None
+        active = self._active(active)
         with torch.cuda.device(self.device):
             if want_stats:
-                stats = torch.empty((self.B, n_periods, nat.N_STATS), dtype=torch.float64,
-                                    device=self.device)
+                stats = (torch.empty if active is None else torch.zeros)(
+                    (self.B, n_periods, nat.N_STATS), dtype=torch.float64, device=self.device)
             if tape is not None:
                 self._check_tape(tape, n_periods)
             a = self._args(n_periods, self.flags | nat.FLAG_BURNIN, stats=stats, tape=tape,
-                           want_io=False)
+                           want_io=False, active=active)
             nat.check(self._lib.cats_step(C.byref(a)))
         self.periods_done += n_periods
         return stats
 
     def step(self, actions: torch.Tensor | None = None, mask: torch.Tensor | None = None,
              burnin: bool = False, want_stats: bool = False, tape: torch.Tensor | None = None,
-             stop_phase: int = 0, debug: torch.Tensor | None = None):
+             stop_phase: int = 0, debug: torch.Tensor | None = None, active: torch.Tensor | None = None):
         """One period for every economy with RL actions (device tensors, zero copies).
+        `active` ([B] bool/uint8 CUDA tensor): only those economies advance; the observation, reward
+        and terminated entries of the others keep their previous values.
 
         actions: float64 [B, n_agents, 2] (production factor, price factor); mask: uint8/bool
         [B, n_agents], False = "dummy" action (cats.py:439-440).  Returns
@@ -204,17 +232,42 @@ class BatchedCats:
         else:
             actions, mask = None, None
         stats = None
+        active = self._active(active)
         with torch.cuda.device(self.device):
             if want_stats:
-                stats = torch.empty((self.B, 1, nat.N_STATS), dtype=torch.float64, device=self.device)
+                stats = (torch.empty if active is None else torch.zeros)(
+                    (self.B, 1, nat.N_STATS), dtype=torch.float64, device=self.device)
             if tape is not None:
                 self._check_tape(tape, 1)
             a = self._args(1, flags, actions=actions, mask=mask, stats=stats, tape=tape,
-                           stop_phase=stop_phase, debug=debug)
+                           stop_phase=stop_phase, debug=debug, active=active)
             nat.check(self._lib.cats_step(C.byref(a)))
         self.periods_done += 1
         nA = self.n_agents
         return self._obs[:, :nA], self._reward[:, :nA], self._terminated, stats
+
+    def observation(self) -> torch.Tensor:
+        """The [B, n_agents, 2] observation buffer the last `step` / `observe` filled (a view)."""
+        return self._obs[:, :self.n_agents]
+
+    def observe(self, active: torch.Tensor | None = None) -> torch.Tensor:
+        """`_get_obs` (cats.py:466-481, 655-671) from the current state without advancing it -- only
+        needed when there is no burn-in step to take the observation from.  Torch arithmetic on the
+        state views: exact in linear mode, `torch.log` in log mode."""
+        nA = self.n_agents
+        yp, yd, p = (self.field(k)[:, :nA] for k in ("c_Y_prev", "c_Yd", "c_P"))
+        ap = self.scalar("price").unsqueeze(1)
+        if self.log_mode:
+            new = torch.stack([torch.log(yp + 1e-8) - torch.log(yd + 1e-8),
+                               torch.log(p + 1e-8) - torch.log(ap + 1e-8)], -1)
+        else:
+            new = torch.stack([yp - yd, p - ap], -1)
+        if active is None:
+            self._obs[:, :nA] = new
+        else:
+            m = self._active(active).to(torch.bool).view(self.B, 1, 1)
+            self._obs[:, :nA] = torch.where(m, new, self._obs[:, :nA])
+        return self._obs[:, :nA]
 
     def step_host(self, actions_host: torch.Tensor | None, mask_host: torch.Tensor | None = None,
                   want_stats: bool = True):
@@ -287,6 +340,6 @@ SCAL_NAMES = [
     "gdp_deflator", "inflationRate", "Un", "consumption", "totK", "bankruptcy_rate", "bank_E",
     "bank_loans", "profitsB", "dividendsB", "bank_interest_income", "bank_bad_debt", "gov_bonds",
     "GB", "deficitGDP", "gov_TA", "gov_G", "gov_r_b", "gov_subsidy_level", "terminated", "status",
-    "reserved0", "reserved1", "reserved2",
+    "episode", "reserved1", "reserved2",
 ]
 SCAL_INDEX = {n: i for i, n in enumerate(SCAL_NAMES)}

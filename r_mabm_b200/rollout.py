@@ -106,21 +106,39 @@ class BatchedQPolicy:
 
 
 class BatchedRollout:
-    """env step + policy + TD update on device for B economies (BASELINE.json config 4)."""
+    """env step + policy + TD update on device for B economies (BASELINE.json config 4).
 
-    def __init__(self, env: BatchedCats, policy: BatchedQPolicy, t_burnin: int = 300, T: int = 1000):
+    `auto_reset=True` gives every economy its own episode clock, as `Simulation.run_episode`
+    (simulation.py:123-149) does for the one economy of the reference: an economy that is terminated or
+    has run its T steps gets a new model and its burn-in (`BatchedCats.reset_where`) while the others
+    carry on, all without a host synchronisation; its next observation is the one `Cats.reset` would
+    return.  `episodes` counts finished episodes per economy."""
+
+    def __init__(self, env: BatchedCats, policy: BatchedQPolicy, t_burnin: int = 300, T: int = 1000,
+                 auto_reset: bool = False):
         self.env, self.policy, self.t_burnin, self.T = env, policy, t_burnin, T
+        self.auto_reset = auto_reset
         self.t = 0
         self.obs = None
+        self.t_b = torch.zeros(env.B, dtype=torch.int32, device=env.device)        # steps into the episode
+        self.episodes = torch.zeros(env.B, dtype=torch.int32, device=env.device)   # finished episodes
+
+    def _burnin(self, active: torch.Tensor | None = None) -> None:
+        """t_burnin heuristic periods (cats.py:423-432); the last one is launched with outputs, so
+        the observation buffer holds what `Cats.reset` returns (`_get_obs` of the burnt-in state)."""
+        if self.t_burnin > 1:
+            self.env.run(self.t_burnin - 1, active=active)
+        if self.t_burnin > 0:
+            self.env.step(burnin=True, active=active)
+        else:
+            self.env.observe(active=active)
 
     def reset(self, seed: int | None = None) -> torch.Tensor:
         self.env.reset_state(seed)
-        if self.t_burnin:
-            self.env.run(self.t_burnin)
+        self._burnin()
         self.t = 0
-        # first observation: a burn-in step with outputs (actions ignored)
-        obs, _, _, _ = self.env.step(burnin=True)
-        self.obs = obs.clone()
+        self.t_b.zero_(); self.episodes.zero_()
+        self.obs = self.env.observation().clone()
         return self.obs
 
     def step(self, train: bool = True):
@@ -129,8 +147,18 @@ class BatchedRollout:
         obs, reward, terminated, _ = self.env.step(actions)
         if train:
             self.policy.train(reward, obs, terminated)
-        self.obs = obs.clone()
         self.t += 1
+        if self.auto_reset:
+            reward, terminated = reward.clone(), terminated.clone()   # the burn-in below reuses the buffers
+            self.t_b += 1
+            done = terminated.to(torch.bool) | (self.t_b >= self.T)
+            self.last_done = done
+            self.env.reset_where(done)
+            self._burnin(active=done)
+            self.t_b.masked_fill_(done, 0)
+            self.episodes += done.to(torch.int32)
+            obs = self.env.observation()
+        self.obs = obs.clone()
         return reward, terminated
 
     def run(self, n_steps: int, train: bool = True) -> torch.Tensor:

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_layout_queries():
     lib = nat.load()
-    assert lib.cats_abi_version() == 1
+    assert lib.cats_abi_version() == nat.ABI_VERSION == 2
     blob = int(lib.cats_blob_bytes(1000, 100, 20))
     assert blob % 128 == 0 and 35000 < blob < 45000
     names = nat.field_names()
@@ -71,4 +71,5 @@ def test_argument_errors_without_a_gpu():
     assert lib.cats_step(C.byref(a)) == nat.EINVAL            # null blobs
     assert b"null" in lib.cats_last_error()
     assert lib.cats_init(None, 1, 1000, 100, 20, None, 0, None) == nat.EINVAL
+    assert lib.cats_reset_masked(None, 1, 1000, 100, 20, None, 0, None, None) == nat.EINVAL
     assert int(lib.cats_host_scratch_bytes(16, 2, 1)) >= 16 * (2 * 16 + 2 + 2 * 16 + 2 * 8 + 1 + 4 + 128)

@@ -82,9 +82,9 @@ def test_config4_marl_rollout_env_policy_and_td_update_on_device():
     obs0 = ro.reset(seed=31).clone()
     refs = make_oracles(B, W, F, N, seed=31)
     for o in refs:
-        for _ in range(20):
+        for _ in range(20):                                   # exactly t_burnin periods, as Cats.reset
             o.step()
-    first = [o.step(actions=[[1.0, 1.0]] * A, mask=[0] * A, flags=orc.FLAG_LOG | orc.FLAG_BURNIN)[0] for o in refs]
+    first = [o.obs(A, orc.FLAG_LOG) for o in refs]
     assert np.array_equal(bits(obs0.cpu().numpy()), bits(np.stack(first)))
     launches0 = env._lib.cats_launch_count()
     for t in range(10):
@@ -114,3 +114,77 @@ def test_config4_marl_rollout_env_policy_and_td_update_on_device():
         del obs_prev
     assert env._lib.cats_launch_count() - launches0 == 10     # one period-kernel launch per rollout step
     assert compare_state(env, refs, "after rollout") == []
+
+
+def test_rollout_auto_reset_gives_every_economy_its_own_episode_clock():
+    """8(f) rank 3: per-economy reset on truncation, on the device.  Economies are knocked out of step
+    by one masked reset, then the rollout runs past several truncations; an oracle per economy follows
+    the same actions and is reset (new model, episode + 1, t_burnin periods) when its clock runs out."""
+    from r_mabm_b200.environments import Cats
+    from r_mabm_b200.rollout import BatchedQPolicy, BatchedRollout
+    BL = dict(Cats._default_gym_spaces_bounds)
+    B, A, W, F, N, T, TB = 5, 2, 300, 30, 6, 4, 6
+    env = _env(B, W=W, F=F, N=N, n_agents=A, seed=13)
+    pol = BatchedQPolicy(B, A, BL, epsilon=1.0, device="cuda", seed=4)
+    ro = BatchedRollout(env, pol, t_burnin=TB, T=T, auto_reset=True)
+    ro.reset(seed=13)
+    refs = make_oracles(B, W, F, N, seed=13)
+    for o in refs:
+        for _ in range(TB):
+            o.step()
+    clock = [0] * B
+    # stagger: economies 1 and 3 start a new episode two steps in
+    for t in range(11):
+        if t == 2:
+            m = torch.tensor([0, 1, 0, 1, 0], dtype=torch.bool, device="cuda")
+            env.reset_where(m, 0); ro._burnin(active=m); ro.t_b.masked_fill_(m, 0)
+            ro.obs = env.observation().clone()
+            for b in (1, 3):
+                refs[b].reset(); clock[b] = 0
+                for _ in range(TB):
+                    refs[b].step()
+        reward, term = ro.step(train=True)
+        torch.cuda.synchronize()
+        acts = ro.last_actions.cpu().numpy()
+        done = ro.last_done.cpu().numpy()
+        for b, o in enumerate(refs):
+            r_obs, r_rew = o.step(actions=acts[b], mask=[1] * A, flags=0)
+            assert np.array_equal(bits(reward[b].cpu().numpy()), bits(r_rew)), (t, b)
+            clock[b] += 1
+            assert bool(done[b]) == (clock[b] >= T)
+            if clock[b] >= T:
+                o.reset(); clock[b] = 0
+                for _ in range(TB):
+                    o.step()
+                r_obs = o.obs(A, 0)
+            assert np.array_equal(bits(ro.obs[b].cpu().numpy()), bits(r_obs)), (t, b)
+        assert compare_state(env, refs, f"t={t}") == []
+    assert ro.episodes.cpu().tolist() == [2, 2, 2, 2, 2]
+    ep = env.scalar("episode").cpu().tolist()
+    assert ep == [2.0, 3.0, 2.0, 3.0, 2.0]
+    # a new episode is a new draw: economy 0 after its reset is not its first episode over again
+    first = make_oracles(1, W, F, N, seed=13)[0]
+    again = make_oracles(1, W, F, N, seed=13)[0]
+    again.reset()
+    for _ in range(TB):
+        first.step(); again.step()
+    assert not np.array_equal(first.i32("Oc"), again.i32("Oc"))
+
+
+def test_active_mask_leaves_the_other_economies_untouched():
+    B, W, F, N = 9, 300, 30, 6
+    env = _env(B, W=W, F=F, N=N, seed=2)
+    env.run(8)
+    before = env.blobs.clone()
+    m = torch.tensor([1, 0, 0, 1, 1, 0, 1, 0, 0], dtype=torch.uint8, device="cuda")
+    stats = env.run(5, want_stats=True, active=m)
+    torch.cuda.synchronize()
+    refs = make_oracles(B, W, F, N, seed=2)
+    for b, o in enumerate(refs):
+        for _ in range(8 + (5 if m[b] else 0)):
+            o.step()
+    assert compare_state(env, refs, "masked run") == []
+    idle = (m == 0).nonzero().flatten().tolist()
+    for b in idle:
+        assert torch.equal(env.blobs[b], before[b]) and float(stats[b].abs().sum()) == 0.0
+    assert float(stats[0, -1, 2]) == refs[0].scal("Un")

@@ -181,3 +181,23 @@ def test_macro_aggregates_are_in_a_plausible_range_over_seeds():
     assert (un < 0.25).all() and un.mean() < 0.12
     assert (yreal > 1200).all() and (yreal < 2300).all()
     assert (np.abs(infl) < 0.05).all()
+
+
+def test_oracle_reset_starts_a_new_episode_with_a_fresh_stream():
+    """oracle_reset == a new model in place with episode + 1; episode 0 is what the goldens pin."""
+    a = orc.OracleEconomy(120, 12, 4, seed=3, economy=1)
+    b = orc.OracleEconomy(120, 12, 4, seed=3, economy=1)
+    for _ in range(5):
+        a.step()
+    a.reset()
+    assert a.scal("episode") == 1.0 and a.scal("timestep") == 0.0
+    fresh = b.snapshot()
+    again = a.snapshot()
+    for k in fresh:
+        if k != "scal":
+            assert np.array_equal(fresh[k], again[k]), k        # same initial state ...
+    for _ in range(5):
+        a.step(); b.step()
+    assert not np.array_equal(a.i32("Oc"), b.i32("Oc"))         # ... different draws
+    a.reset()
+    assert a.scal("episode") == 2.0

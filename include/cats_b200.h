@@ -171,6 +171,12 @@ void cats_debug_phase_cycles(void *d_cycles16);
  * block share nothing but their start time; tests/ run every shape. */
 void cats_debug_set_group(int economies_per_block);
 
+/* Debug aid: economies of the reference's default size (W=1000, F=100, N=20) with all z <= 5 run a
+ * kernel instantiation whose state layout is a compile-time constant (addresses are base + immediate,
+ * loop bounds are known: ~18 % fewer instructions).  0 makes later cats_step calls use the generic
+ * kernel for them too; 1 (default) restores the specialisation.  Results never depend on it. */
+void cats_debug_set_static(int on);
+
 #ifdef __cplusplus
 }
 #endif

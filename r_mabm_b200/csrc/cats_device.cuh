@@ -204,9 +204,9 @@ struct OrderKeys {
     uint32_t k[4], a, b, m, n;
     const int *tape_order;
 };
-inline OrderDims make_order_dims(int n)
+__host__ __device__ constexpr OrderDims make_order_dims(int n)
 {
-    OrderDims d; uint32_t a = 1;
+    OrderDims d{}; uint32_t a = 1;
     while ((uint64_t)a * a < (uint64_t)n) ++a;
     d.a = a; d.b = ((uint32_t)n + a - 1) / a; d.n = (uint32_t)n;
     d.m = d.b > 1 ? (uint32_t)(((uint64_t)1 << 32) / d.b) + 1u : 0u;   // mulhi32(x, m) == x / b for x < 2^23
@@ -219,8 +219,21 @@ __device__ __forceinline__ uint32_t perm_hash(uint32_t v, uint32_t k)
     x *= 0x85EBCA6Bu;   // only the high bits of x are used (mulhi by the half-domain size)
     return x;
 }
-struct Order {
+// NS > 0: the market size is a compile-time constant (default-size economies) and so are the network
+// dimensions; NS == 0: they are read from the keys block.
+template <uint32_t NS>
+struct OrderT {
     volatile OrderKeys *k;
+    struct Dims { uint32_t a, b, m, n; };
+    __device__ __forceinline__ Dims dims() const
+    {
+        if constexpr (NS > 0) {
+            constexpr OrderDims d = make_order_dims((int)NS);
+            return Dims{d.a, d.b, d.m, d.n};
+        } else {
+            return Dims{k->a, k->b, k->m, k->n};
+        }
+    }
     __device__ __forceinline__ void init(const Draws &d, int market, const OrderDims &dims, OrderKeys *keys, int lane)
     {
         k = keys;
@@ -241,7 +254,8 @@ struct Order {
     {
         const int *to = k->tape_order;
         if (to) return to[pos];
-        const uint32_t a = k->a, b = k->b, m = k->m, n = k->n;
+        const Dims dm = dims();
+        const uint32_t a = dm.a, b = dm.b, m = dm.m, n = dm.n;
         const uint32_t k0 = k->k[0], k1 = k->k[1], k2 = k->k[2], k3 = k->k[3];
         uint32_t x = (uint32_t)pos;
         do {
@@ -259,7 +273,8 @@ struct Order {
     // order, cycle-walked the same way).  Only for the keyed bijection, not for a tape order.
     __device__ __forceinline__ int position_of(int who) const
     {
-        const uint32_t a = k->a, b = k->b, m = k->m, n = k->n;
+        const Dims dm = dims();
+        const uint32_t a = dm.a, b = dm.b, m = dm.m, n = dm.n;
         const uint32_t k0 = k->k[0], k1 = k->k[1], k2 = k->k[2], k3 = k->k[3];
         uint32_t x = (uint32_t)who;
         do {

@@ -65,7 +65,14 @@ struct KArgs {
 
 // per-warp view of the working set.  Only two base pointers are kept: every section address is
 // base + a constant-bank offset, recomputed where it is used (registers are what bounds residency).
-struct Ctx {
+// ST: the economy has the default size and the layout is a compile-time constant (DefaultLayout)
+template <bool ST>
+struct CtxT {
+    static constexpr bool kStatic = ST;
+    __device__ __forceinline__ decltype(auto) layout() const
+    {
+        if constexpr (ST) return DefaultLayout{}; else return (a->L);
+    }
     unsigned char *sm;    // shared-memory working set
     unsigned char *blob;  // this economy's blob in global memory (Oc, C-firm rows, cold K rows, PA, perm live there)
     const KArgs *a;
@@ -74,28 +81,28 @@ struct Ctx {
     int last;             // last phase id to execute (stop_phase or 99)
     Draws d;
     __device__ __forceinline__ unsigned lt() const { return (1u << lane) - 1u; }   // lanes below this one
-    __device__ __forceinline__ double *scal() const { return reinterpret_cast<double *>(sm + a->L.o_scal); }
-    __device__ __forceinline__ double *par() const { return reinterpret_cast<double *>(sm + a->L.s_par); }
-    __device__ __forceinline__ int *Leff() const { return reinterpret_cast<int *>(sm + a->L.o_Leff); }
-    __device__ __forceinline__ int *vac() const { return reinterpret_cast<int *>(sm + a->L.s_vac); }   // Ld == Leff + vac
-    __device__ __forceinline__ unsigned *emp() const { return reinterpret_cast<unsigned *>(sm + a->L.s_emp); }
-    __device__ __forceinline__ int *misc() const { return reinterpret_cast<int *>(sm + a->L.s_misc); }
-    __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + a->L.s_misc + 16); }
-    __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + a->L.s_misc + 56); }
-    __device__ __forceinline__ int *Oc() const { return reinterpret_cast<int *>(blob + a->L.o_Oc); }          // GLOBAL
+    __device__ __forceinline__ double *scal() const { return reinterpret_cast<double *>(sm + layout().o_scal); }
+    __device__ __forceinline__ double *par() const { return reinterpret_cast<double *>(sm + layout().s_par); }
+    __device__ __forceinline__ int *Leff() const { return reinterpret_cast<int *>(sm + layout().o_Leff); }
+    __device__ __forceinline__ int *vac() const { return reinterpret_cast<int *>(sm + layout().s_vac); }   // Ld == Leff + vac
+    __device__ __forceinline__ unsigned *emp() const { return reinterpret_cast<unsigned *>(sm + layout().s_emp); }
+    __device__ __forceinline__ int *misc() const { return reinterpret_cast<int *>(sm + layout().s_misc); }
+    __device__ __forceinline__ OrderKeys *okeys() const { return reinterpret_cast<OrderKeys *>(sm + layout().s_misc + 16); }
+    __device__ __forceinline__ volatile double *gk() const { return reinterpret_cast<volatile double *>(sm + layout().s_misc + 56); }
+    __device__ __forceinline__ int *Oc() const { return reinterpret_cast<int *>(blob + layout().o_Oc); }          // GLOBAL
     // households: {wealth, permanent income} records, GLOBAL
-    __device__ __forceinline__ double2 *hh() const { return reinterpret_cast<double2 *>(blob + a->L.o_PA); }
+    __device__ __forceinline__ double2 *hh() const { return reinterpret_cast<double2 *>(blob + layout().o_PA); }
     __device__ __forceinline__ double &PA(int h) const { return hh()[h].x; }
     __device__ __forceinline__ double &perm(int h) const { return hh()[h].y; }
     __device__ __forceinline__ int z_c() const { return (int)par()[P_z_c]; }
     __device__ __forceinline__ int z_k() const { return (int)par()[P_z_k]; }
     __device__ __forceinline__ int z_e() const { return (int)par()[P_z_e]; }
-    __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + a->L.o_c + field * a->L.rowF); }  // GLOBAL
+    __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + layout().o_c + field * layout().rowF); }  // GLOBAL
     // K-firm rows: hot ones (P, Yd, Q) are SHARED, the others GLOBAL; `field` is a compile-time constant
     __device__ __forceinline__ double *kf(int field) const
     {
-        return field < NK_HOT ? reinterpret_cast<double *>(sm + a->L.o_kh + field * a->L.rowN)
-                              : reinterpret_cast<double *>(blob + a->L.o_kc + (field - NK_HOT) * a->L.rowN);
+        return field < NK_HOT ? reinterpret_cast<double *>(sm + layout().o_kh + field * layout().rowN)
+                              : reinterpret_cast<double *>(blob + layout().o_kc + (field - NK_HOT) * layout().rowN);
     }
     __device__ __forceinline__ double *at(int off) const { return reinterpret_cast<double *>(sm + off); }
     __device__ __forceinline__ int *iat(int off) const { return reinterpret_cast<int *>(sm + off); }
@@ -119,7 +126,8 @@ __device__ __forceinline__ int bfly_i(int a)
 
 // ---------------------------------------------------------------------------------------------
 // a8 firms_get_credit! for one firm (cats.py:376-377)
-__device__ __forceinline__ void credit_one(const Ctx &c, double need, double b1, double b2, double &deb,
+template <class C>
+__device__ __forceinline__ void credit_one(const C &c, double need, double b1, double b2, double &deb,
                                            double A, double &interest_r, double &Ftot, double liquidity,
                                            int &Ld, int Leff, int &vac)
 {
@@ -155,9 +163,10 @@ __device__ __forceinline__ void credit_one(const Ctx &c, double need, double b1,
 
 // a3-a8: every per-firm decision of the period in one pass (phases 3..10).  No cross-firm
 // dependence: the bank rations against its start-of-period equity.
-__device__ void phase_firm_decisions(Ctx &c)
+template <class C>
+__device__ void phase_firm_decisions(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int F = L.F, N = L.N, last = c.last;
     const double alpha = c.par()[P_alpha], q_adj = c.par()[P_q_adj], p_adj = c.par()[P_p_adj];
     const double wb = c.scal()[S_wb];
@@ -286,9 +295,10 @@ __device__ void phase_firm_decisions(Ctx &c)
 // employees with the smallest (fire_key, worker index).  The employees of the over-staffed firms
 // are bucketed by firm (count, prefix, scatter) and every pooled worker ranks itself inside its
 // firm's bucket; rank < s means dismissed.  The result does not depend on the bucket order.
-__device__ void phase_fire(Ctx &c, int limit)
+template <class C>
+__device__ void phase_fire(C &c, int limit)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int W = L.W, lane = c.lane;
     int *ic = c.iat(L.s_ic);    // per firm: pooled head-count (low 16 bits) | pool cursor (high 16 bits)
     // pooled head-count of an over-staffed firm == its Leff (#{w : Oc[w] == f} == Leff[f] is an invariant)
@@ -386,13 +396,13 @@ __device__ void phase_fire(Ctx &c, int limit)
 // the longest prefix of lanes whose picks cannot have been pre-empted by a lower lane is committed
 // at once (lane j is safe iff fewer than vac[f] lower lanes chose the same f), the rest retry
 // against the updated vacancies.  Outcome == the sequential visiting-order rule.
-template <int ZM>
-__device__ void phase_job_search(Ctx &c)
+template <int ZM, class C>
+__device__ void phase_job_search(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int W = L.W, nf = L.F + L.N, lane = c.lane;
     const int z = c.z_e() < nf ? c.z_e() : nf;
-    Order ord; ord.init(c.d, MKT_JOB, c.a->od[MKT_JOB], c.okeys(), lane);
+    OrderT<C::kStatic ? DefaultLayout::kW : 0> ord; ord.init(c.d, MKT_JOB, c.a->od[MKT_JOB], c.okeys(), lane);
     unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
     int total = 0;
     // Few seekers (the usual case: unemployment of a few percent): list them with one coalesced pass
@@ -513,9 +523,10 @@ struct Mkt {
 };
 
 // a11 firms_produce! (cats.py:384-385)
-__device__ void phase_produce(Ctx &c)
+template <class C>
+__device__ void phase_produce(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int F = L.F, N = L.N, last = c.last;
     const double alpha = c.par()[P_alpha], k = c.par()[P_k], eta = c.par()[P_eta], theta = c.par()[P_theta];
     const double wb = c.scal()[S_wb], pk = c.scal()[S_price_k];
@@ -587,13 +598,13 @@ __device__ void phase_produce(Ctx &c)
 // a12 capital_goods_market! (cats.py:387).  The investing C-firms are compacted in visiting order;
 // 32 of them at a time draw and price-sort their z_k suppliers in parallel and then trade one after
 // the other (there are ~F * Iprob buyers per period: a short chain).
-template <int ZM>
-__device__ void phase_capital_market(Ctx &c)
+template <int ZM, class C>
+__device__ void phase_capital_market(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int F = L.F, N = L.N, lane = c.lane;
     const int z = c.z_k() < N ? c.z_k() : N;
-    Order ord; ord.init(c.d, MKT_CAP, c.a->od[MKT_CAP], c.okeys(), lane);
+    OrderT<C::kStatic ? DefaultLayout::kF : 0> ord; ord.init(c.d, MKT_CAP, c.a->od[MKT_CAP], c.okeys(), lane);
     double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Ysk = c.at(L.s_kYstock);
     const double *RPk = c.kf(K_Q);   // 1 / P, parked there by phase_produce
     double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
@@ -667,9 +678,10 @@ __device__ void phase_capital_market(Ctx &c)
 // a13 gov_adjusts_subsidy! (cats.py:389) and the government side of a14 workers_get_paid!
 // (cats.py:391): subsidy level, wage tax and subsidy totals.  The employed head-count is the sum
 // of Leff (== #{Oc >= 0}: invariant kept by firing, job search and bankruptcy).
-__device__ void phase_gov_income(Ctx &c)
+template <class C>
+__device__ void phase_gov_income(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     int n = 0;
     for (int i = c.lane; i < L.F + L.N; i += 32) n += c.Leff()[i];
     n = bfly_i(n);
@@ -691,9 +703,10 @@ __device__ void phase_gov_income(Ctx &c)
 }
 
 // debug path only (stop_phase 18 / 19): the household rules without the market
-__device__ void phase_households_only(Ctx &c)
+template <class C>
+__device__ void phase_households_only(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
     const double xi = c.par()[P_xi], chi = c.par()[P_chi];
     for (int h = c.lane; h < L.H; h += 32) {
@@ -727,16 +740,16 @@ __device__ void phase_households_only(Ctx &c)
 //       including the first lane that exhausts its seller is committed; that lane (with what is left
 //       of its budget) and the lanes queued behind it at the exhausted seller walk on in the next
 //       round.  Stock, sales and budgets therefore follow the visiting order exactly.
-template <int ZM>
-__device__ void phase_goods_market(Ctx &c)
+template <int ZM, class C>
+__device__ void phase_goods_market(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int W = L.W, F = L.F, H = L.H, lane = c.lane;
     const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
     Mkt mkt(c.sm + L.s_U, F);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
-    Order ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
+    OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0> ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
     // market constants: computed once, parked in shared memory and re-read per chunk (registers)
     enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
@@ -888,9 +901,10 @@ __device__ void phase_goods_market(Ctx &c)
 }
 
 // a17 firms_accounting! (cats.py:397-398)
-__device__ void phase_accounting(Ctx &c)
+template <class C>
+__device__ void phase_accounting(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int W = L.W, F = L.F, N = L.N, last = c.last;
     const double delta = c.par()[P_delta], eta = c.par()[P_eta], k = c.par()[P_k], theta = c.par()[P_theta];
     const double divs = c.par()[P_div], taxd = c.par()[P_tax_rate_d];
@@ -967,11 +981,12 @@ __device__ void phase_accounting(Ctx &c)
 }
 
 // a18 Cats._get_reward (cats.py:493-556), evaluated between accounting and tracking
-__device__ void phase_reward(Ctx &c)
+template <class C>
+__device__ void phase_reward(C &c)
 {
     const KArgs &a = *c.a;
     if (!a.reward || a.n_agents <= 0) return;
-    const int F = a.L.F, nA = a.n_agents;
+    const int F = c.layout().F, nA = a.n_agents;
     const double *P = c.cf(C_P), *Q = c.cf(C_Q);
     if (a.flags & CATS_FLAG_REWARD_RMS) {
         // cats.py:548-549: Python sum() over the RL firms, then over the others, left to right
@@ -1004,9 +1019,10 @@ __device__ void phase_reward(Ctx &c)
 }
 
 // a19 update_tracking_variables! (cats.py:401)
-__device__ void phase_tracking(Ctx &c)
+template <class C>
+__device__ void phase_tracking(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int F = L.F, N = L.N;
     const double *cP = c.cf(C_P), *cQ = c.cf(C_Q), *cY = c.cf(C_Y_prev), *cK = c.cf(C_K);
     double sQ = 0.0, sPQ = 0.0, sP = 0.0, sY = 0.0, sK = 0.0, sQk = 0.0, sPQk = 0.0, sYk = 0.0;
@@ -1043,9 +1059,10 @@ __device__ void phase_tracking(Ctx &c)
 }
 
 // a20 firms_go_bankrupt! (cats.py:404) + a21 _get_terminated (cats.py:483-486)
-__device__ void phase_bankrupt(Ctx &c)
+template <class C>
+__device__ void phase_bankrupt(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int W = L.W, F = L.F, N = L.N;
     const double thr = c.par()[P_E_threshold_scale] * c.scal()[S_price];
     unsigned char *bad = c.sm + L.s_bad;
@@ -1153,9 +1170,10 @@ __device__ void phase_bankrupt(Ctx &c)
 }
 
 // a22 bank_accounting!, a23 gov_accounting!, a24 adjust_wages!, a25 timestep (cats.py:407-413)
-__device__ void phase_closing(Ctx &c)
+template <class C>
+__device__ void phase_closing(C &c)
 {
-    const Layout &L = c.a->L;
+    const auto &L = c.layout();
     const int last = c.last;
     double share = 0.0;
     if (c.lane == 0) {
@@ -1188,11 +1206,12 @@ __device__ void phase_closing(Ctx &c)
 
 // ---------------------------------------------------------------------------------------------
 // one period; phase ids as docs/MODEL.md section 6 (stop_phase halts after the given id)
-template <int ZM, int G>
-__device__ void run_period(Ctx &c)
+template <int ZM, int G, class C>
+__device__ void run_period(C &c)
 {
     const KArgs &a = *c.a;
-    const int F = a.L.F, N = a.L.N, last = c.last;
+    const auto &L = c.layout();
+    const int F = L.F, N = L.N, last = c.last;
 #ifdef CATS_PROFILE_PHASES
     long long t0 = 0;
     const bool prof = a.cycles && c.lane == 0 && c.b == 0;
@@ -1227,7 +1246,7 @@ __device__ void run_period(Ctx &c)
     phase_capital_market<ZM>(c);  // 16
     // household wealth / permanent income are first touched by the goods market: into L2 just ahead
     // of it (any earlier and the lines age out of L2 again before they are used)
-    if (c.lane == 0 && last >= 18) bulk_prefetch_l2(c.blob + a.L.o_PA, (uint32_t)(a.L.blob - a.L.o_PA));
+    if (c.lane == 0 && last >= 18) bulk_prefetch_l2(c.blob + L.o_PA, (uint32_t)(L.blob - L.o_PA));
     TICK(4);
     if (last < 17) return;
     phase_gov_income(c);      // 17 (+ government side of 18)
@@ -1267,14 +1286,18 @@ __device__ void run_period(Ctx &c)
 // MASKED: the launch honours KArgs::active (per-economy resets).  A separate instantiation, so that
 // the test at the kernel entry cannot disturb the register allocation of the common, unmasked path
 // (measured: the same source with the test compiled in is 3 % slower even when active == nullptr).
-template <int ZM, int G, int MINB, bool MASKED>
+// ST: default-size economies, layout folded into the code (DefaultLayout); the host picks it when
+// (W, F, N) == (1000, 100, 20) and the slice is not padded.
+template <int ZM, int G, int MINB, bool MASKED, bool ST>
 __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_block[];
-    const Layout &L = a.L;
-    unsigned char *smem = smem_block + (size_t)(threadIdx.x >> 5) * (size_t)a.slice;
-    Ctx c;
-    c.sm = smem; c.a = &a;
+    CtxT<ST> c;
+    c.a = &a;
+    const auto &L = c.layout();
+    const int slice = ST ? ((DefaultLayout::smem + 15) & ~15) : a.slice;
+    unsigned char *smem = smem_block + (size_t)(threadIdx.x >> 5) * (size_t)slice;
+    c.sm = smem;
     c.lane = threadIdx.x & 31;
     c.last = a.stop_phase > 0 ? a.stop_phase : 99;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.s_misc + 8);
@@ -1451,6 +1474,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 static int g_group = 0;                // debug: set by cats_debug_set_group() (0 = automatic)
+static int g_static = 1;               // debug: cats_debug_set_static(0) keeps the generic kernel for the default size
 constexpr int kThreads = 32;    // one warp per economy
 // economies resident per SM that the register budget is cut for (__launch_bounds__): 28 x 32 threads
 // x 72 registers fill the register file; shared memory (8.2 KB per default-size economy) allows the same
@@ -1463,23 +1487,29 @@ static int smem_pad()
     if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
     return pad;
 }
-template <int ZM, bool MASKED>
+template <int ZM, bool MASKED, bool ST>
 static KernelFn select_group(int g)
 {
     switch (g) {
-    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2, MASKED>;
-    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4, MASKED>;
-    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8, MASKED>;
-    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12, MASKED>;
-    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14, MASKED>;
-    default: return cats_period_kernel<ZM, 1, kMaxPerSM, MASKED>;
+    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2, MASKED, ST>;
+    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4, MASKED, ST>;
+    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8, MASKED, ST>;
+    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12, MASKED, ST>;
+    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14, MASKED, ST>;
+    default: return cats_period_kernel<ZM, 1, kMaxPerSM, MASKED, ST>;
     }
 }
-static KernelFn select_kernel(int max_z, int g, bool masked = false)
+static bool is_default_size(const Layout &L)
 {
-    if (masked) return select_group<MAX_Z, true>(g);   // resets are rare: one instantiation serves every z
-    if (max_z > 0 && max_z <= 5) return select_group<5, false>(g);
-    return select_group<MAX_Z, false>(g);
+    static int off = -1;   // development aid: CATS_NO_STATIC=1 keeps the generic kernel for every size
+    if (off < 0) { const char *e = getenv("CATS_NO_STATIC"); off = e ? atoi(e) : 0; }
+    return !off && g_static && L.W == DefaultLayout::kW && L.F == DefaultLayout::kF && L.N == DefaultLayout::kN && smem_pad() == 0;
+}
+static KernelFn select_kernel(const Layout &L, int max_z, int g, bool masked = false)
+{
+    if (masked) return select_group<MAX_Z, true, false>(g);   // resets are rare: one instantiation serves every size and z
+    if (max_z > 0 && max_z <= 5) return is_default_size(L) ? select_group<5, false, true>(g) : select_group<5, false, false>(g);
+    return select_group<MAX_Z, false, false>(g);
 }
 static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 15) & ~15; }
 // Economies per block (see cats_period_kernel).  Shared memory and the register file bound how many
@@ -1551,6 +1581,8 @@ const char *cats_last_error(void) { return g_err; }
 uint64_t cats_launch_count(void) { return g_launches.load(); }
 void cats_debug_phase_cycles(void *d_cycles16) { g_cycles = (long long *)d_cycles16; }
 void cats_debug_set_group(int economies_per_block) { g_group = economies_per_block; }
+
+void cats_debug_set_static(int on) { g_static = on ? 1 : 0; }
 
 size_t cats_blob_bytes(int W, int F, int N)
 {
@@ -1667,7 +1699,7 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int g = choose_group(L, 1ll << 40, nsm);   // the shape of a launch that fills the GPU
-    if (int rc = configure_kernel(L, select_kernel(5, g), g, &occ, &sms)) return rc;
+    if (int rc = configure_kernel(L, select_kernel(L, 5, g), g, &occ, &sms)) return rc;
     if (threads) *threads = kThreads * g;            // per block: g economies, one warp each
     if (smem_bytes) *smem_bytes = slice_bytes(L) * g;
     if (blocks_per_sm) *blocks_per_sm = occ;
@@ -1750,7 +1782,7 @@ int cats_step(const cats_step_args *s)
     const int g = choose_group(a.L, s->B, nsm);
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
-    KernelFn fn = select_kernel(s->max_z, g, s->d_active != nullptr);
+    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr);
     if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
     fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
     g_launches++;

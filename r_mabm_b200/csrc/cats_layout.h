@@ -71,11 +71,11 @@ struct Layout {
     int32_t d_Ld, d_vac, d_cFtot, d_cKdem, d_cYstock, d_cvalinv, d_kFtot, d_kYstock, workset;
 };
 
-__host__ __device__ inline int32_t up16(int64_t x) { return (int32_t)((x + 15) & ~(int64_t)15); }
+__host__ __device__ constexpr int32_t up16(int64_t x) { return (int32_t)((x + 15) & ~(int64_t)15); }
 
-inline Layout make_layout(int W, int F, int N)
+constexpr Layout make_layout(int W, int F, int N)
 {
-    Layout L;
+    Layout L{};
     L.W = W; L.F = F; L.N = N; L.H = W + F + N;
     L.rowF = up16(8ll * F); L.rowN = up16(8ll * N);
     int64_t o = 0;
@@ -124,6 +124,55 @@ inline Layout make_layout(int W, int F, int N)
     L.workset = (int32_t)o;
     return L;
 }
+
+
+// The reference's default economy (W=1000, F=100, N=20: cats.py:115-117, every BASELINE configuration
+// but the 10x one) with the layout resolved at compile time: the same member names as `Layout`, as
+// static constants, so that `L.F`, `L.o_c`, ... in the phase code fold into immediates (addresses
+// become base + immediate, loops get constant bounds).
+struct DefaultLayout {
+    static constexpr int kW = 1000, kF = 100, kN = 20;
+    static constexpr Layout k = make_layout(kW, kF, kN);
+    static constexpr int32_t W = k.W;
+    static constexpr int32_t F = k.F;
+    static constexpr int32_t N = k.N;
+    static constexpr int32_t H = k.H;
+    static constexpr int32_t rowF = k.rowF;
+    static constexpr int32_t rowN = k.rowN;
+    static constexpr int32_t o_scal = k.o_scal;
+    static constexpr int32_t o_kh = k.o_kh;
+    static constexpr int32_t o_Leff = k.o_Leff;
+    static constexpr int32_t resident = k.resident;
+    static constexpr int32_t o_Oc = k.o_Oc;
+    static constexpr int32_t o_c = k.o_c;
+    static constexpr int32_t o_kc = k.o_kc;
+    static constexpr int32_t o_PA = k.o_PA;
+    static constexpr int32_t o_perm = k.o_perm;
+    static constexpr int32_t blob = k.blob;
+    static constexpr int32_t s_vac = k.s_vac;
+    static constexpr int32_t s_cFtot = k.s_cFtot;
+    static constexpr int32_t s_cKdem = k.s_cKdem;
+    static constexpr int32_t s_cvalinv = k.s_cvalinv;
+    static constexpr int32_t s_kFtot = k.s_kFtot;
+    static constexpr int32_t s_kYstock = k.s_kYstock;
+    static constexpr int32_t s_ic = k.s_ic;
+    static constexpr int32_t s_bad = k.s_bad;
+    static constexpr int32_t s_U = k.s_U;
+    static constexpr int32_t U_bytes = k.U_bytes;
+    static constexpr int32_t s_emp = k.s_emp;
+    static constexpr int32_t s_par = k.s_par;
+    static constexpr int32_t s_misc = k.s_misc;
+    static constexpr int32_t smem = k.smem;
+    static constexpr int32_t d_Ld = k.d_Ld;
+    static constexpr int32_t d_vac = k.d_vac;
+    static constexpr int32_t d_cFtot = k.d_cFtot;
+    static constexpr int32_t d_cKdem = k.d_cKdem;
+    static constexpr int32_t d_cYstock = k.d_cYstock;
+    static constexpr int32_t d_cvalinv = k.d_cvalinv;
+    static constexpr int32_t d_kFtot = k.d_kFtot;
+    static constexpr int32_t d_kYstock = k.d_kYstock;
+    static constexpr int32_t workset = k.workset;
+};
 
 struct TapeOff {
     uint32_t u_price_c, u_price_k, u_invest, fire_key, job_order, job_cand, cap_order, cap_cand,

@@ -102,3 +102,32 @@ def test_block_shape_never_changes_results():
                 assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), f"group {g}"
     finally:
         lib.cats_debug_set_group(0)
+
+
+def test_static_layout_kernel_equals_the_generic_kernel_at_the_default_size():
+    """Default-size economies run a kernel whose layout is a compile-time constant.
+    The generic instantiation, every block shape, RL actions, statistics and a masked launch (always
+    generic) give the same bits."""
+    from r_mabm_b200 import _native as nat
+    from r_mabm_b200.engine import BatchedCats
+    lib = nat.load()
+    ref = None
+    try:
+        for static, g in ((1, 0), (0, 0), (1, 8), (0, 8), (1, 1), (1, 12)):
+            lib.cats_debug_set_static(static); lib.cats_debug_set_group(g)
+            env = BatchedCats(31, n_agents=2, seed=19)          # W=1000, F=100, N=20
+            env.run(9)
+            acts = torch.full((31, 2, 2), 0.97, dtype=torch.float64, device="cuda")
+            obs, rew, term, st1 = env.step(acts, torch.ones((31, 2), dtype=torch.uint8, device="cuda"), want_stats=True)
+            obs, rew = obs.clone(), rew.clone()
+            stats = env.run(4, want_stats=True)
+            env.run(2, active=torch.ones(31, dtype=torch.uint8, device="cuda"))
+            torch.cuda.synchronize()
+            got = (env.blobs.clone(), stats.clone(), obs, rew, st1.clone())
+            if ref is None:
+                ref = got
+            else:
+                for a, b in zip(got, ref):
+                    assert torch.equal(a, b), f"static={static} group={g}"
+    finally:
+        lib.cats_debug_set_static(1); lib.cats_debug_set_group(0)

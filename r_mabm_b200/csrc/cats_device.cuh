@@ -133,7 +133,10 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
 }
 
 // the draw source of one economy-period
-struct Draws {
+// TAPE = false: the instantiation never reads a tape (the `tape` member is dead and costs nothing)
+template <bool TAPE>
+struct DrawsT {
+    static constexpr bool kTape = TAPE;
     const unsigned char *tape;  // nullptr => Philox
     uint32_t k0, k1, period, economy;
     const TapeOff *tp;          // tape record layout (kernel parameter space: costs no registers)
@@ -145,7 +148,7 @@ struct Draws {
     }
     __device__ __forceinline__ double uniform(uint32_t phase, int agent) const
     {
-        if (tape) {
+        if (TAPE && tape) {
             uint32_t off = phase == PH_PRICE_C ? tp->u_price_c : phase == PH_PRICE_K ? tp->u_price_k : tp->u_invest;
             return *reinterpret_cast<const double *>(tape + off + 8u * (uint32_t)agent);
         }
@@ -154,14 +157,14 @@ struct Draws {
     }
     __device__ __forceinline__ uint32_t fire_key(int worker) const
     {
-        if (tape) return *reinterpret_cast<const uint32_t *>(tape + tp->fire_key + 4u * (uint32_t)worker);
+        if (TAPE && tape) return *reinterpret_cast<const uint32_t *>(tape + tp->fire_key + 4u * (uint32_t)worker);
         return philox((uint32_t)worker, PH_FIRE, 0).x;
     }
     // z <= 8 distinct indices in [0,n): partial Fisher-Yates on a virtual identity array (register only)
     template <int ZM>
     __device__ __forceinline__ void candidates(uint32_t phase, int agent, int n, int z, int (&out)[ZM]) const
     {
-        if (tape) {
+        if (TAPE && tape) {
             uint32_t off; int zz;
             if (phase == PH_JOB) { off = tp->job_cand; zz = tape_z[2]; }
             else if (phase == PH_CAP) { off = tp->cap_cand; zz = tape_z[1]; }
@@ -221,7 +224,7 @@ __device__ __forceinline__ uint32_t perm_hash(uint32_t v, uint32_t k)
 }
 // NS > 0: the market size is a compile-time constant (default-size economies) and so are the network
 // dimensions; NS == 0: they are read from the keys block.
-template <uint32_t NS>
+template <uint32_t NS, bool TAPE>
 struct OrderT {
     volatile OrderKeys *k;
     struct Dims { uint32_t a, b, m, n; };
@@ -234,13 +237,14 @@ struct OrderT {
             return Dims{k->a, k->b, k->m, k->n};
         }
     }
-    __device__ __forceinline__ void init(const Draws &d, int market, const OrderDims &dims, OrderKeys *keys, int lane)
+    template <class D>
+    __device__ __forceinline__ void init(const D &d, int market, const OrderDims &dims, OrderKeys *keys, int lane)
     {
         k = keys;
         if (lane == 0) {
             keys->a = dims.a; keys->b = dims.b; keys->m = dims.m; keys->n = dims.n;
             keys->tape_order = nullptr;
-            if (d.tape) {
+            if (TAPE && d.tape) {
                 uint32_t off = market == MKT_JOB ? d.tp->job_order : market == MKT_CAP ? d.tp->cap_order : d.tp->goods_order;
                 keys->tape_order = reinterpret_cast<const int *>(d.tape + off);
             } else {
@@ -252,8 +256,10 @@ struct OrderT {
     }
     __device__ __forceinline__ int at(int pos) const
     {
-        const int *to = k->tape_order;
-        if (to) return to[pos];
+        if (TAPE) {
+            const int *to = k->tape_order;
+            if (to) return to[pos];
+        }
         const Dims dm = dims();
         const uint32_t a = dm.a, b = dm.b, m = dm.m, n = dm.n;
         const uint32_t k0 = k->k[0], k1 = k->k[1], k2 = k->k[2], k3 = k->k[3];
@@ -289,7 +295,7 @@ struct OrderT {
         } while (x >= n);
         return (int)x;
     }
-    __device__ __forceinline__ bool from_tape() const { return k->tape_order != nullptr; }
+    __device__ __forceinline__ bool from_tape() const { return TAPE && k->tape_order != nullptr; }
 };
 
 // stable ascending sort of ZM (candidate, price) pairs by price, register only: a sorting network

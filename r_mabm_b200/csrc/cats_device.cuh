@@ -112,16 +112,18 @@ __device__ __forceinline__ int warp_int_sum(int n, int lane, Fn val)
 
 // ---------------------------------------------------------------------------------------------
 // Philox-4x32-10
+// rk: the 10 round keys {k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85}, expanded once on the host into the
+// kernel's parameter block: a round is two wide multiplies and two three-input xors whose key operand
+// comes straight from the constant bank (no key-schedule adds, no key registers).
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1)
+                                               const uint32_t *rk)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -138,13 +140,14 @@ template <bool TAPE>
 struct DrawsT {
     static constexpr bool kTape = TAPE;
     const unsigned char *tape;  // nullptr => Philox
-    uint32_t k0, k1, period, economy;
+    const uint32_t *rk;         // Philox round keys (kernel parameter space)
+    uint32_t period, economy;
     const TapeOff *tp;          // tape record layout (kernel parameter space: costs no registers)
     const int *tape_z;          // z_c, z_k, z_e the tape was laid out with
 
     __device__ __forceinline__ uint4 philox(uint32_t agent, uint32_t phase, uint32_t block) const
     {
-        return philox4x32_10(agent, (phase << 8) | block, period, economy, k0, k1);
+        return philox4x32_10(agent, (phase << 8) | block, period, economy, rk);
     }
     __device__ __forceinline__ double uniform(uint32_t phase, int agent) const
     {

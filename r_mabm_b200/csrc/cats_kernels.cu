@@ -336,7 +336,10 @@ int cats_step(const cats_step_args *s)
     a.tape_z[0] = a.tape_z[1] = a.tape_z[2] = 0;
     a.blobs = (unsigned char *)s->d_blobs; a.B = s->B;
     a.params = s->d_params; a.params_stride = s->params_stride;
-    a.k0 = (uint32_t)s->seed; a.k1 = (uint32_t)(s->seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) {
+        a.rk[2 * r] = (uint32_t)s->seed + r * 0x9E3779B9u;
+        a.rk[2 * r + 1] = (uint32_t)(s->seed >> 32) + r * 0xBB67AE85u;
+    }
     a.economy_base = s->economy_base;
     a.n_periods = s->n_periods; a.flags = s->flags; a.n_agents = s->n_agents;
     a.actions = s->d_actions; a.mask = s->d_action_mask;

@@ -38,7 +38,7 @@ struct KArgs {
     long long B;
     const double *params;
     long long params_stride;
-    uint32_t k0, k1;
+    uint32_t rk[20];   // Philox round keys: {seed_lo + r * 0x9E3779B9, seed_hi + r * 0xBB67AE85}, r = 0..9
     unsigned long long economy_base;
     int n_periods;
     unsigned flags;
@@ -1350,7 +1350,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     if (c.lane == 0) c.misc()[M_EPISODE] = (int)((uint32_t)c.scal()[S_episode] << 20);
     __syncwarp();
 
-    c.d.k0 = a.k0; c.d.k1 = a.k1;
+    c.d.rk = a.rk;
     c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
     c.d.tp = &a.T;
     c.d.tape_z = a.tape_z;

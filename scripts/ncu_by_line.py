@@ -6,8 +6,8 @@ nep = float(sys.argv[5]) if len(sys.argv) > 5 else 0
 import tempfile, os
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 off2line = {}
 cur = None; infn = False
 for ln in dis:
@@ -34,7 +34,7 @@ for r in rows[hi + 1:]:
     agg[key][0] += int(r[ie]); agg[key][1] += int(r[ss])
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 src = {}
-for f in ("cats_kernels.cu", "cats_device.cuh"):
+for f in ("cats_kernels.cu", "cats_period.cuh", "cats_device.cuh"):
     try: src[f] = open(os.path.join(os.path.dirname(so), "csrc", f)).read().splitlines()
     except Exception: src[f] = []
 print(f"total warp-inst {ti}  samples {ts}")

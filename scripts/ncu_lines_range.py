@@ -6,8 +6,8 @@ for a in sys.argv[5:]:
     f, r = a.split(":"); lo, hi = r.split("-"); ranges.append((f, int(lo), int(hi)))
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 off2line = {}; cur = None; infn = False
 for ln in dis:
     if ln.startswith(".text."): infn = kern in ln; continue

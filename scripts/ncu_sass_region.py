@@ -3,8 +3,8 @@ import csv, re, subprocess, sys, os, tempfile
 rep, so, kern, fname, lo, hi = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]), int(sys.argv[6])
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 off2line = {}; cur = None; infn = False
 for ln in dis:
     if ln.startswith(".text."): infn = kern in ln; continue

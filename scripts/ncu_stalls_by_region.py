@@ -3,8 +3,8 @@ import csv, re, subprocess, sys, collections, os, tempfile
 rep, so, kern, nep = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3], float(sys.argv[4])
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 off2line = {}; cur = None; infn = False
 for ln in dis:
     if ln.startswith(".text."): infn = kern in ln; continue
@@ -20,7 +20,7 @@ def regions(path):
         if m and not l.strip().startswith("//"): out.append((i, m.group(1)))
     return out
 src_dir = "/root/repo/r_mabm_b200/csrc"
-regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_device.cuh")}
+regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_period.cuh", "cats_device.cuh")}
 def region(key):
     if key is None: return "?"
     f, line = key

@@ -3,8 +3,8 @@ import re, subprocess, sys, os, tempfile, collections
 so, kern = sys.argv[1], sys.argv[2]
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 def regions(path):
     out = []
     for i, l in enumerate(open(path).read().splitlines(), 1):
@@ -12,7 +12,7 @@ def regions(path):
         if m and not l.strip().startswith("//"): out.append((i, m.group(1)))
     return out
 src_dir = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc") if os.path.isdir(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc")) else "/root/repo/r_mabm_b200/csrc"
-regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_device.cuh")}
+regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_period.cuh", "cats_device.cuh")}
 def region(key):
     if key is None: return "?"
     f, line = key

@@ -3,8 +3,8 @@ import re, subprocess, sys, os, tempfile
 so, kern, lo, hi = os.path.abspath(sys.argv[1]), sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
+dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 cur = None; infn = False; addrs = []
 for ln in dis:
     if ln.startswith(".text."): infn = kern in ln; continue

@@ -1,10 +1,11 @@
-// cats_kernels.cu -- the batched CATS economy period kernel for sm_100a and its C-ABI.
+// cats_period.cuh -- the batched CATS economy period kernel for sm_100a.
 //
-// One WARP = one economy (one 32-thread block per economy, ~20 resident per SM).  The resident
-// prefix of the economy blob is pulled from HBM into shared memory with a single TMA bulk copy
-// (cp.async.bulk + mbarrier), the economy is advanced n_periods periods, and the prefix is pushed
-// back with a bulk store; the tail of the blob (employment links, C-firm rows, household wealth) is
-// streamed through L2.  Phase order is the order of Cats.step
+// One WARP = one economy; G economies share a block (448 threads at the default size, 28 economies
+// resident per SM) only so that they start together and walk the period code in step (see
+// cats_period_kernel).  The resident prefix of the economy blob is pulled from HBM into shared memory
+// with a single TMA bulk copy (cp.async.bulk + mbarrier), the economy is advanced n_periods periods,
+// and the prefix is pushed back with a bulk store; the tail of the blob (employment links, C-firm
+// rows, household records) is streamed through L2.  Phase order is the order of Cats.step
 // (/root/reference/rmabm/environments/cats.py:355-419); every rule is docs/MODEL.md.
 //
 // Parallel structure inside a warp
@@ -17,8 +18,11 @@
 //     longest prefix of lanes whose outcome cannot depend on an uncommitted one is committed at
 //     once.  A round ends at the first buyer that exhausts a seller; the outcome is exactly the
 //     sequential visiting-order market of the reference, including the order of every fp64 add.
-//   - no block-level barrier anywhere: a warp never waits for another warp.
-#include <cuda_runtime.h>
+//   - the warps of a block exchange no data; block barriers only re-align them (once per period and
+//     once before the closing phases).
+//
+// Compiled in three modes (CtxT<MODE>): 0 = every feature, 1 = production (Philox only, no debug
+// stop), 2 = production with the default-size layout as compile-time constants.  DESIGN.md 2.2b.
 #ifndef CATS_PERIOD_CUH
 #define CATS_PERIOD_CUH
 #include <cuda_runtime.h>

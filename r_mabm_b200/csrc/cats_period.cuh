@@ -746,6 +746,44 @@ __device__ void phase_households_only(C &c)
     __syncwarp();
 }
 
+// A household's sorted candidate list, consumed front to back by the goods-market walk: (seller + 1)
+// per slot, 0 = end of list.  Generic: 16 bits per slot in two 64-bit words (F <= 16383).  SMALL (the
+// seller count is a compile-time constant <= 254): 8 bits per slot in two 32-bit words -- half the
+// registers, and a pop is a mask, a funnel shift and a shift.
+template <bool SMALL> struct CandList;
+template <> struct CandList<false> {
+    unsigned long long w0 = 0ull, w1 = 0ull;
+    __device__ __forceinline__ void set(int k, unsigned seller)
+    {
+        if (k < 4) w0 |= (unsigned long long)(seller + 1u) << (16 * k);
+        else w1 |= (unsigned long long)(seller + 1u) << (16 * (k - 4));
+    }
+    __device__ __forceinline__ bool pop(int &seller)
+    {
+        const unsigned e = (unsigned)(w0 & 0xffffull);
+        if (e == 0u) return false;
+        seller = (int)e - 1;
+        w0 = (w0 >> 16) | (w1 << 48); w1 >>= 16;
+        return true;
+    }
+};
+template <> struct CandList<true> {
+    unsigned w0 = 0u, w1 = 0u;
+    __device__ __forceinline__ void set(int k, unsigned seller)
+    {
+        if (k < 4) w0 |= (seller + 1u) << (8 * k);
+        else w1 |= (seller + 1u) << (8 * (k - 4));
+    }
+    __device__ __forceinline__ bool pop(int &seller)
+    {
+        const unsigned e = w0 & 0xffu;
+        if (e == 0u) return false;
+        seller = (int)e - 1;
+        w0 = __funnelshift_r(w0, w1, 8); w1 >>= 8;
+        return true;
+    }
+};
+
 // a14 + a15 + a16: workers_get_paid!, households_find_cons_budget!, consumption_goods_market!
 // (cats.py:391-394), fused.  Households are visited in the market's random order, 32 at a time.
 //   prepare (lane-parallel): gather wealth / permanent income / employment link (prefetched one
@@ -818,8 +856,8 @@ __device__ void phase_goods_market(C &c)
             pa = pa - b;
             c.perm(h) = pm;
         }
-        // a16: candidates, sorted by price, packed 16 bits each
-        unsigned long long cp0 = 0ull, cp1 = 0ull;
+        // a16: candidates, sorted by price, packed
+        CandList<C::kStatic && DefaultLayout::kF <= 254> cl;
         unsigned pend = __ballot_sync(FULL, b > 0.0);
         if (b > 0.0) {
             int cand[ZM]; unsigned key[ZM];
@@ -830,15 +868,13 @@ __device__ void phase_goods_market(C &c)
                 key[k] = k < z ? (mkt.cls[cand[k]] << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
             sort_keys<ZM>(key);
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) {
-                if (k < 4) cp0 |= (unsigned long long)(key[k] & 0x3fffu) << (16 * k);
-                else cp1 |= (unsigned long long)(key[k] & 0x3fffu) << (16 * (k - 4));
-            }
+            for (int k = 0; k < ZM; ++k)
+                if (k < z) cl.set(k, key[k] & 0x3fffu);
         }
         // term: the seller this lane will buy from (>= 0), TERM_NONE (nothing left to visit / done)
         // or TERM_WALK (has budget and must walk down its list to the next seller with stock)
         enum { TERM_NONE = -1, TERM_WALK = -2 };
-        int nrem = b > 0.0 ? z : 0, term = b > 0.0 ? TERM_WALK : TERM_NONE;
+        int term = b > 0.0 ? TERM_WALK : TERM_NONE;
         double d_t = 0.0;
         unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
         while (pend) {
@@ -847,10 +883,9 @@ __device__ void phase_goods_market(C &c)
             // exhausted a seller -- so the test comes after the step)
             do {
                 if (term == TERM_WALK) {
-                    if (nrem == 0) term = TERM_NONE;   // every candidate is sold out
+                    int cnd;
+                    if (!cl.pop(cnd)) term = TERM_NONE;   // every candidate is sold out
                     else {
-                        const int cnd = (int)(cp0 & 0xffffull);
-                        cp0 = (cp0 >> 16) | (cp1 << 48); cp1 >>= 16; --nrem;
                         const double2 yr = mkt.yr[cnd];   // stock, 1 / price
                         fx_red(&acc[cnd], xb);
                         if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }

@@ -2,6 +2,9 @@
 `Simulation`, `QLearner`, `Dummy`, `Logger`) and records what it returns:
 
     python tests/golden/make_reference_driver.py      ->  tests/golden/reference_driver.npz
+    python tests/golden/make_reference_driver.py --reference-tests
+        runs the reference's OWN test-suite (/root/reference/tests, unmodified, 33 tests) over the same
+        stand-ins: a check that they honour the protocol the reference expects (33 passed).
 
 The reference's Python layer needs two packages this image does not have: `gymnasium` (only its
 `Env` base class, `spaces.Box/Dict` and `register`) and `juliacall` (the bridge to ABCredit.jl).  Both
@@ -55,21 +58,43 @@ def install_fake_gymnasium():
         def reset(self, seed=None, options=None):
             return None
 
+        @property
+        def unwrapped(self):
+            return self
+
+        def get_wrapper_attr(self, name):
+            return getattr(self, name)
+
     class Box:
         def __init__(self, low, high, shape=None, dtype=np.float32):
-            self.low, self.high = low, high
+            self.low, self.high, self.shape = low, high, shape or (1,)
+
+        def sample(self):
+            return np.random.uniform(self.low, self.high, size=self.shape).astype(np.float32)
 
     class Dict_(dict):
+        shape = None          # as in gymnasium: a Dict space has no shape (heuristic.py:30 relies on it)
+
         def __init__(self, spaces_):
             super().__init__(spaces_)
             self.spaces = dict(spaces_)
+
+        def sample(self):
+            return {k: v.sample() for k, v in self.spaces.items()}
 
     spaces = types.ModuleType("gymnasium.spaces")
     spaces.Box, spaces.Dict = Box, Dict_
     core = types.ModuleType("gymnasium.core")
     core.ObsType = core.ActType = core.RenderFrame = object
     gym.Env, gym.spaces, gym.core = Env, spaces, core
-    gym.register = lambda **kw: None
+    registry = {}
+    gym.register = lambda id, entry_point, **kw: registry.__setitem__(id, entry_point)
+
+    def make(id, **kwargs):     # no wrappers: the tests only go through .unwrapped / get_wrapper_attr
+        import importlib
+        mod, cls = registry[id].split(":")
+        return getattr(importlib.import_module(mod), cls)(**kwargs)
+    gym.make = make
     sys.modules.update({"gymnasium": gym, "gymnasium.spaces": spaces, "gymnasium.core": core})
 
 
@@ -342,6 +367,10 @@ def main():
     install_fake_gymnasium()
     install_fake_juliacall()
     sys.path.insert(0, str(REFERENCE))
+    if "--reference-tests" in sys.argv:
+        import pytest
+        raise SystemExit(pytest.main([str(REFERENCE / "tests"), "-p", "no:cacheprovider", "-q",
+                                      "--rootdir", str(REFERENCE)]))
     import rmabm                     # the real reference package
     assert Path(rmabm.__file__).resolve().is_relative_to(REFERENCE)
     out: dict[str, np.ndarray] = {}

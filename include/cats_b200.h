@@ -140,6 +140,41 @@ int cats_step(const cats_step_args *args);
 size_t cats_host_scratch_bytes(int64_t B, int n_agents, int n_periods);
 int cats_step_host(const cats_step_args *args_with_host_io, void *d_scratch);
 
+/* ---- learned firms: tabular Q-learning policy, one table per (economy, agent) --------------------
+ * The batched twin of rmabm.agents.QLearner (/root/reference/rmabm/agents/qlearners.py:63-166) as ONE
+ * launch per rollout step: the TD(0) update for the transition just observed (`train`,
+ * qlearners.py:130-166), then the epsilon-greedy choice for the new observation (`get_action`,
+ * qlearners.py:97-128).  Observations, rewards and actions are the device buffers cats_step reads and
+ * writes: nothing leaves the GPU.
+ *   binning: index of the nearest of n poles linearly spaced over [lo, hi]; the lower pole wins a tie,
+ *            values outside clamp, NaN -> 0 (qlearners.py:63-95)
+ *   train:   Q[s,a] += alpha * ((r + (terminated ? 0 : gamma * max Q[s', .])) - Q[s,a])
+ *   act:     one Philox-4x32-10 block per (economy, agent, step): counter (agent, 0x51, step, global
+ *            economy id), key = seed;  explore <=> w0 * 2^-32 < epsilon, then a0 = mulhi(w1, n2),
+ *            a1 = mulhi(w2, n3); otherwise the first argmax of Q[s', ., .].  The action values are
+ *            lo + index * (hi - lo) / (n - 1), as qlearners.py:121-126. */
+typedef struct cats_q_args {
+    double *d_Q;                 /* [B][A][n0][n1][n2][n3] in/out */
+    int64_t B;
+    int32_t A;
+    int32_t n[4];                /* bins: firm_stock, price_delta, production factor, price factor (each >= 2) */
+    double obs_lo[2], obs_hi[2]; /* gym_spaces_bounds obs_firm_stock / obs_price_delta (cats.py:106-111) */
+    double act_lo[2], act_hi[2]; /* act_production_factor / act_price_factor */
+    double alpha, gamma, epsilon;
+    uint64_t seed;
+    uint64_t economy_base;       /* global id of economy 0 of this call */
+    uint32_t step;               /* rollout step counter (exploration stream position) */
+    int32_t do_train, do_act;
+    const double *d_obs;         /* [B][A][2]: the observation AFTER the step (s'); the state to act on */
+    const double *d_reward;      /* [B][A]  (train only) */
+    const uint8_t *d_terminated; /* [B]     (train only) */
+    int32_t *d_last;             /* [B][A][4] in/out: (s0, s1, a0, a1) of the action in flight */
+    double *d_actions;           /* out [B][A][2] (act only): feeds cats_step_args.d_actions */
+    const uint8_t *d_active;     /* [B] or NULL: economies with a zero entry are skipped */
+    void *stream;
+} cats_q_args;
+int cats_q_step(const cats_q_args *args);
+
 /* Size of the on-chip working set image written to d_debug (blob + transients). */
 size_t cats_workset_bytes(int W, int F, int N);
 /* Element stride of a named state field, in elements of its dtype: 1 for contiguous rows, 2 for

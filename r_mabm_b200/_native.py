@@ -31,7 +31,7 @@ STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_t
 EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
     "cats_field_stride",
-    "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_reset_masked", "cats_step", "cats_host_scratch_bytes",
+    "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_reset_masked", "cats_step", "cats_q_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
     "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group", "cats_debug_set_static",
 ]
@@ -52,6 +52,18 @@ class StepArgs(C.Structure):
         ("d_stats", C.c_void_p), ("d_tape", C.c_void_p), ("tape_z", C.c_int32 * 3),
         ("max_z", C.c_int32), ("stop_phase", C.c_int32), ("d_debug", C.c_void_p), ("stream", C.c_void_p),
         ("d_active", C.c_void_p),
+    ]
+
+
+class QArgs(C.Structure):
+    """struct cats_q_args (include/cats_b200.h)."""
+    _fields_ = [
+        ("d_Q", C.c_void_p), ("B", C.c_int64), ("A", C.c_int32), ("n", C.c_int32 * 4),
+        ("obs_lo", C.c_double * 2), ("obs_hi", C.c_double * 2), ("act_lo", C.c_double * 2),
+        ("act_hi", C.c_double * 2), ("alpha", C.c_double), ("gamma", C.c_double), ("epsilon", C.c_double),
+        ("seed", C.c_uint64), ("economy_base", C.c_uint64), ("step", C.c_uint32), ("do_train", C.c_int32),
+        ("do_act", C.c_int32), ("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p),
+        ("d_last", C.c_void_p), ("d_actions", C.c_void_p), ("d_active", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 
@@ -90,6 +102,7 @@ def load() -> C.CDLL:
     L.cats_reset_masked.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p]
     L.cats_step.argtypes = [C.POINTER(StepArgs)]
+    L.cats_q_step.argtypes = [C.POINTER(QArgs)]
     L.cats_host_scratch_bytes.restype = C.c_size_t
     L.cats_host_scratch_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
     L.cats_step_host.argtypes = [C.POINTER(StepArgs), C.c_void_p]

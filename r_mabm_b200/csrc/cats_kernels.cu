@@ -53,6 +53,84 @@ __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, co
     for (int w = tid; w < L.W; w += nt) Oc[w] = -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tabular Q policy (cats_q_step): one warp per (economy, agent).  The row Q[s', ., .] is read once for
+// the bootstrap maximum; the TD update touches one cell; the greedy choice re-reads the row only when
+// the updated cell lies in it (s == s').
+struct QArgs {
+    double *Q; long long B; int A; int n[4];
+    double obs_lo[2], obs_step[2], act_lo[2], act_hi[2];
+    double alpha, gamma, epsilon;
+    uint32_t rk[20];
+    unsigned long long economy_base; uint32_t step; int do_train, do_act;
+    const double *obs, *reward; const unsigned char *terminated; int *last; double *actions;
+    const unsigned char *active;
+};
+
+__device__ __forceinline__ int q_bin(double x, double lo, double step, int n)
+{
+    double idx = ceil((x - lo) / step - 0.5);
+    if (idx != idx) idx = 0.0;                       // NaN -> 0
+    if (idx < 0.0) idx = 0.0;
+    if (idx > (double)(n - 1)) idx = (double)(n - 1);
+    return (int)idx;
+}
+
+// (max value, first index of it) over row[0, m): lanes stride, then a butterfly on (value, index)
+__device__ __forceinline__ void q_row_max(const double *row, int m, int lane, double &best, int &arg)
+{
+    best = -__longlong_as_double(0x7ff0000000000000LL) * 1.0; arg = 0x7fffffff;
+    best = __longlong_as_double(0xfff0000000000000LL);
+    for (int i = lane; i < m; i += 32) {
+        const double v = row[i];
+        if (v > best || (v == best && i < arg)) { best = v; arg = i; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, best, off);
+        const int oa = __shfl_xor_sync(FULL, arg, off);
+        if (ov > best || (ov == best && oa < arg)) { best = ov; arg = oa; }
+    }
+}
+
+__global__ void cats_q_kernel(const __grid_constant__ QArgs q)
+{
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (economy, agent) pair
+    const int lane = threadIdx.x & 31;
+    if (w >= q.B * q.A) return;
+    const long long b = w / q.A; const int a = (int)(w % q.A);
+    if (q.active && !q.active[b]) return;
+    const int n0 = q.n[0], n1 = q.n[1], n2 = q.n[2], n3 = q.n[3], m = n2 * n3;
+    double *Qa = q.Q + (size_t)w * (size_t)n0 * (size_t)n1 * (size_t)m;
+    const double o0 = q.obs[2 * w], o1 = q.obs[2 * w + 1];
+    const int s0n = q_bin(o0, q.obs_lo[0], q.obs_step[0], n0), s1n = q_bin(o1, q.obs_lo[1], q.obs_step[1], n1);
+    double *row = Qa + ((size_t)s0n * n1 + s1n) * m;
+    double best; int arg;
+    q_row_max(row, m, lane, best, arg);
+    int *last = q.last + 4 * w;
+    if (q.do_train) {
+        const int s0 = last[0], s1 = last[1], a0 = last[2], a1 = last[3];
+        __syncwarp();
+        if (lane == 0) {
+            const double boot = q.terminated[b] ? 0.0 : q.gamma * best;
+            const double target = q.reward[w] + boot;
+            double *cell = Qa + (((size_t)s0 * n1 + s1) * n2 + a0) * n3 + a1;
+            const double cur = *cell;
+            *cell = cur + q.alpha * (target - cur);
+        }
+        __syncwarp();
+        if (q.do_act && s0 == s0n && s1 == s1n) q_row_max(row, m, lane, best, arg);   // the row changed
+    }
+    if (q.do_act && lane == 0) {
+        const uint4 r = philox4x32_10((uint32_t)a, 0x51u, q.step, (uint32_t)(q.economy_base + (unsigned long long)b), q.rk);
+        int a0 = arg / n3, a1 = arg - a0 * n3;
+        if ((double)r.x * (1.0 / 4294967296.0) < q.epsilon) { a0 = (int)__umulhi(r.y, (uint32_t)n2); a1 = (int)__umulhi(r.z, (uint32_t)n3); }
+        last[0] = s0n; last[1] = s1n; last[2] = a0; last[3] = a1;
+        q.actions[2 * w] = q.act_lo[0] + (double)a0 * (q.act_hi[0] - q.act_lo[0]) / (double)(n2 - 1);
+        q.actions[2 * w + 1] = q.act_lo[1] + (double)a1 * (q.act_hi[1] - q.act_lo[1]) / (double)(n3 - 1);
+    }
+}
+
 }  // namespace cats
 
 // =============================================================================================
@@ -365,6 +443,37 @@ int cats_step(const cats_step_args *s)
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));
+    return CATS_OK;
+}
+
+int cats_q_step(const cats_q_args *s)
+{
+    if (!s) return fail(CATS_EINVAL, "null args%s", "");
+    if (!s->d_Q || !s->d_obs || !s->d_last || s->B < 0 || s->A < 1) return fail(CATS_EINVAL, "cats_q_step: null pointer, negative B or A < 1%s", "");
+    for (int i = 0; i < 4; ++i) if (s->n[i] < 2 || s->n[i] > 4096) return fail(CATS_EINVAL, "cats_q_step: bins must be in [2, 4096]%s", "");
+    if (s->do_train && (!s->d_reward || !s->d_terminated)) return fail(CATS_EINVAL, "cats_q_step: train needs reward and terminated%s", "");
+    if (s->do_act && !s->d_actions) return fail(CATS_EINVAL, "cats_q_step: act needs an action buffer%s", "");
+    if (s->B == 0 || (!s->do_train && !s->do_act)) return CATS_OK;
+    QArgs q;
+    q.Q = s->d_Q; q.B = s->B; q.A = s->A;
+    for (int i = 0; i < 4; ++i) q.n[i] = s->n[i];
+    for (int i = 0; i < 2; ++i) {
+        q.obs_lo[i] = s->obs_lo[i]; q.obs_step[i] = (s->obs_hi[i] - s->obs_lo[i]) / (double)(s->n[i] - 1);
+        q.act_lo[i] = s->act_lo[i]; q.act_hi[i] = s->act_hi[i];
+    }
+    q.alpha = s->alpha; q.gamma = s->gamma; q.epsilon = s->epsilon;
+    for (uint32_t r = 0; r < 10; ++r) {
+        q.rk[2 * r] = (uint32_t)s->seed + r * 0x9E3779B9u;
+        q.rk[2 * r + 1] = (uint32_t)(s->seed >> 32) + r * 0xBB67AE85u;
+    }
+    q.economy_base = s->economy_base; q.step = s->step; q.do_train = s->do_train; q.do_act = s->do_act;
+    q.obs = s->d_obs; q.reward = s->d_reward; q.terminated = s->d_terminated; q.last = s->d_last;
+    q.actions = s->d_actions; q.active = s->d_active;
+    const long long warps = s->B * s->A;
+    cats_q_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)s->stream>>>(q);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_q_step launch: %s", cudaGetErrorString(e));
     return CATS_OK;
 }
 

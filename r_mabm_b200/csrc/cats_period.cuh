@@ -483,7 +483,7 @@ __device__ void phase_job_search(C &c)
         const int idx = base + lane;
         int w = -1;
         int cand[ZM];
-        if (idx < total) { w = (int)seekers[idx]; c.d.candidates<ZM>(PH_JOB, w, nf, z, cand); }
+        if (idx < total) { w = (int)seekers[idx]; c.d.template candidates<ZM>(PH_JOB, w, nf, z, cand); }
         unsigned pending = __ballot_sync(FULL, idx < total);
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
@@ -647,7 +647,7 @@ __device__ void phase_capital_market(C &c)
         if (act) {
             f = buyers[idx]; kd = Kdem[f]; lq = liq[f];
             cb = (Ftot[f] + lq) - wages[f];
-            c.d.candidates<ZM>(PH_CAP, f, N, z, cand);
+            c.d.template candidates<ZM>(PH_CAP, f, N, z, cand);
 #pragma unroll
             for (int k = 0; k < ZM; ++k) if (k < z) pr[k] = Pk[cand[k]];
             sort_by_price<ZM>(cand, pr, z);
@@ -861,7 +861,7 @@ __device__ void phase_goods_market(C &c)
         unsigned pend = __ballot_sync(FULL, b > 0.0);
         if (b > 0.0) {
             int cand[ZM]; unsigned key[ZM];
-            c.d.candidates<ZM>(PH_GOODS, h, F, z, cand);
+            c.d.template candidates<ZM>(PH_GOODS, h, F, z, cand);
             // key = price class (14 bits) | draw index (3 bits) | seller (14 bits): F <= 16383
 #pragma unroll
             for (int k = 0; k < ZM; ++k)

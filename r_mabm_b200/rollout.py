@@ -105,6 +105,65 @@ class BatchedQPolicy:
         self.Q[self._b, self._a, s0, s1, a0, a1] = cur + self.alpha * (target - cur)
 
 
+class FusedQPolicy(BatchedQPolicy):
+    """The same learners with `train` and `get_action` as ONE hand-written kernel per rollout step
+    (`cats_q_step`, include/cats_b200.h) instead of ~45 torch launches: the rollout of BASELINE.json
+    config 4 is launch-bound otherwise.  Same binning, TD(0) update and greedy rule as `BatchedQPolicy`
+    (qlearners.py:63-166).  Exploration draws come from Philox keyed by (seed, global economy id, agent,
+    step) -- not from a torch generator -- so a rollout is reproducible at any batch size or sharding.
+    CUDA only; `BatchedQPolicy` is the torch twin that also runs on the CPU."""
+
+    def __init__(self, B: int, n_agents: int, bounds: dict, n_bins=(11, 11, 11, 11), alpha: float = 0.1,
+                 gamma: float = 0.99, epsilon: float = 0.9, device="cuda", seed: int = 0, economy_base: int = 0):
+        super().__init__(B, n_agents, bounds, n_bins, alpha, gamma, epsilon, device, seed)
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedQPolicy runs on a CUDA device; use BatchedQPolicy on the CPU")
+        from . import _native as nat
+        self._nat, self._lib = nat, nat.load()
+        self.seed, self.economy_base, self.step_count = int(seed), int(economy_base), 0
+        self.last = torch.zeros((B, n_agents, 4), dtype=torch.int32, device=self.device)
+        self.actions = torch.zeros((B, n_agents, 2), dtype=torch.float64, device=self.device)
+
+    def _launch(self, obs, reward, terminated, do_train: bool, do_act: bool, active=None) -> None:
+        import ctypes as C
+        a = self._nat.QArgs()
+        a.d_Q = self.Q.data_ptr(); a.B = self.B; a.A = self.A
+        for i in range(4):
+            a.n[i] = self.n[i]
+        b = self.bounds
+        a.obs_lo[0], a.obs_hi[0] = b["obs_firm_stock"]; a.obs_lo[1], a.obs_hi[1] = b["obs_price_delta"]
+        a.act_lo[0], a.act_hi[0] = b["act_production_factor"]; a.act_lo[1], a.act_hi[1] = b["act_price_factor"]
+        a.alpha, a.gamma, a.epsilon = self.alpha, self.gamma, self.epsilon
+        a.seed = self.seed & 0xFFFFFFFFFFFFFFFF; a.economy_base = self.economy_base
+        a.step = self.step_count & 0xFFFFFFFF
+        a.do_train, a.do_act = int(do_train), int(do_act)
+        for t in (obs, reward, terminated):
+            if t is not None and not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("FusedQPolicy takes contiguous CUDA tensors")
+        a.d_obs = obs.data_ptr()
+        a.d_reward = reward.data_ptr() if reward is not None else None
+        a.d_terminated = terminated.data_ptr() if terminated is not None else None
+        a.d_last = self.last.data_ptr(); a.d_actions = self.actions.data_ptr()
+        a.d_active = active.data_ptr() if active is not None else None
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._nat.check(self._lib.cats_q_step(C.byref(a)))
+
+    def get_action(self, obs: torch.Tensor, active: torch.Tensor | None = None) -> torch.Tensor:
+        self._launch(obs, None, None, False, True, active)
+        self.step_count += 1
+        return self.actions
+
+    def train(self, reward: torch.Tensor, next_obs: torch.Tensor, terminated: torch.Tensor) -> None:
+        self._launch(next_obs, reward, terminated, True, False)
+
+    def train_and_act(self, reward: torch.Tensor, next_obs: torch.Tensor, terminated: torch.Tensor) -> torch.Tensor:
+        """TD update for the transition that ended in `next_obs`, then the action for it: one launch."""
+        self._launch(next_obs, reward, terminated, True, True)
+        self.step_count += 1
+        return self.actions
+
+
 class BatchedRollout:
     """env step + policy + TD update on device for B economies (BASELINE.json config 4).
 
@@ -120,6 +179,7 @@ class BatchedRollout:
         self.auto_reset = auto_reset
         self.t = 0
         self.obs = None
+        self._next_actions = None
         self.t_b = torch.zeros(env.B, dtype=torch.int32, device=env.device)        # steps into the episode
         self.episodes = torch.zeros(env.B, dtype=torch.int32, device=env.device)   # finished episodes
 
@@ -137,15 +197,24 @@ class BatchedRollout:
         self.env.reset_state(seed)
         self._burnin()
         self.t = 0
+        self._next_actions = None
         self.t_b.zero_(); self.episodes.zero_()
         self.obs = self.env.observation().clone()
         return self.obs
 
     def step(self, train: bool = True):
-        actions = self.policy.get_action(self.obs)
+        fused = train and not self.auto_reset and hasattr(self.policy, "train_and_act")
+        if fused and self._next_actions is not None:
+            actions = self._next_actions          # chosen by the launch that trained on the last transition
+        else:
+            actions = self.policy.get_action(self.obs)
         self.last_actions = actions      # kept for loggers / tests; never leaves the device
         obs, reward, terminated, _ = self.env.step(actions)
-        if train:
+        if fused:
+            # two launches per rollout step: the period kernel, then TD update + next action in one
+            self.last_actions = actions.clone()
+            self._next_actions = self.policy.train_and_act(reward, obs, terminated)
+        elif train:
             self.policy.train(reward, obs, terminated)
         self.t += 1
         if self.auto_reset:

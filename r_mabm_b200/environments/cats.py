@@ -82,8 +82,10 @@ class Cats:
                                    reward_type=reward_type, price_change=price_change,
                                    log_mode=self._log_mode, bankruptcy_reward=float(bankruptcy_reward),
                                    seed=self._seed, device=device)
+        self._alloc_host()
+        self._sync_host()
         # init_price is inserted by initialise_model in the reference (read at cats.py:530)
-        self.params["init_price"] = float(self._engine.scalar("init_price")[0])
+        self.params["init_price"] = self._scal("init_price")
 
         ids_c_firms = [f + 1 for f in range(F)]          # firm_id: 1-based slot index
         self.agents_ids: list[int] = ids_c_firms[:n_agents]
@@ -139,6 +141,7 @@ class Cats:
             self._seed = random.getrandbits(63)          # unseeded reset: a fresh stream, like the reference
         self._engine.reset_state(seed=self._seed)
         self._burnin()
+        self._sync_host()
         return self._get_obs(), self._get_info()
 
     def _burnin(self) -> None:
@@ -150,22 +153,22 @@ class Cats:
         if len(actions) != self.n_agents:
             raise ValueError(
                 f"Number of actions ({len(actions)}) must be equal to the number of agents ({self.n_agents})")
-        import torch
         eng = self._engine
         act_t = mask_t = None
         if self.n_agents > 0 and not burnin:
-            vals = np.ones((1, self.n_agents, 2), dtype=np.float64)
-            mask = np.zeros((1, self.n_agents), dtype=np.uint8)
+            vals, mask = self._h_act.numpy(), self._h_mask.numpy()
+            vals[...] = 1.0; mask[...] = 0
             for i, a in enumerate(actions):
                 if "dummy" in a:                           # cats.py:439-440
                     continue
                 vals[0, i, 0], vals[0, i, 1] = float(a[0]), float(a[1])
                 mask[0, i] = 1
-            act_t = torch.from_numpy(vals).to(eng.device)
-            mask_t = torch.from_numpy(mask).to(eng.device)
+            act_t = self._d_act.copy_(self._h_act, non_blocking=True)
+            mask_t = self._d_mask.copy_(self._h_mask, non_blocking=True)
         obs_t, rew_t, term_t, _ = eng.step(act_t, mask_t, burnin=burnin or self.n_agents == 0)
         self.t += 1
-        status = int(eng._status[0])
+        self._sync_host(obs_t, rew_t, term_t)      # ONE synchronisation per step: state + outputs to the host
+        status = int(self._h_status[0])
         if status:
             import warnings
             from .. import _native as nat
@@ -173,21 +176,58 @@ class Cats:
                 warnings.warn("division by zero in 'depreciation value', setting to 0.")
             if status & nat.STATUS_PROFIT_NAN:
                 warnings.warn("profits are nan (likely underflow), setting to 0.")
-        reward = [float(x) for x in rew_t[0].tolist()] if self.n_agents else []
-        terminated = bool(int(term_t[0]))
-        obs = self._obs_from_tensor(obs_t)
+        n = self.n_agents
+        reward = [float(x) for x in self._h_rew[0, :n].tolist()] if n else []
+        terminated = bool(int(self._h_term[0]))
+        obs = [{"firm_stock": v[0], "price_delta": v[1]} for v in self._h_obs[0, :n].tolist()] if n else []
         info = self._get_info()
         truncated = self.t >= self.T
         return obs, reward, terminated, truncated, info
 
-    def _obs_from_tensor(self, obs_t):
-        if self.n_agents == 0:
-            return []
-        vals = obs_t[0].tolist()
-        return [{"firm_stock": v[0], "price_delta": v[1]} for v in vals]
+    # -- host mirror of the one economy: filled once per step / reset, read by obs / info ---------------
+    def _alloc_host(self) -> None:
+        import torch
+        eng, nA = self._engine, max(self.n_agents, 1)
+        pin = dict(pin_memory=True)
+        self._h_blob = torch.empty((eng.blob_bytes,), dtype=torch.uint8, **pin)
+        self._h_obs = torch.empty((1, nA, 2), dtype=torch.float64, **pin)
+        self._h_rew = torch.empty((1, nA), dtype=torch.float64, **pin)
+        self._h_term = torch.empty((1,), dtype=torch.uint8, **pin)
+        self._h_status = torch.empty((1,), dtype=torch.int32, **pin)
+        self._h_act = torch.ones((1, nA, 2), dtype=torch.float64, **pin)
+        self._h_mask = torch.zeros((1, nA), dtype=torch.uint8, **pin)
+        self._d_act = torch.ones((1, nA, 2), dtype=torch.float64, device=eng.device)
+        self._d_mask = torch.zeros((1, nA), dtype=torch.uint8, device=eng.device)
+        self._h_views: dict = {}
+
+    def _sync_host(self, obs_t=None, rew_t=None, term_t=None) -> None:
+        import torch
+        eng = self._engine
+        self._h_blob.copy_(eng.blobs[0], non_blocking=True)
+        if obs_t is not None and self.n_agents:
+            self._h_obs[:, :self.n_agents].copy_(obs_t, non_blocking=True)
+            self._h_rew[:, :self.n_agents].copy_(rew_t, non_blocking=True)
+        if term_t is not None:
+            self._h_term.copy_(term_t, non_blocking=True)
+        self._h_status.copy_(eng._status, non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
 
     def _field(self, name):
-        return self._engine.field(name)[0].cpu().numpy()
+        """Host view of a named state field of the economy, as of the last step / reset."""
+        v = self._h_views.get(name)
+        if v is None:
+            from .. import _native as nat
+            off, cnt, dt = nat.field_info(self.W, self.F, self.N, name)
+            st = nat.field_stride(name)
+            raw = self._h_blob.numpy()
+            arr = raw.view(np.float64 if dt == 0 else np.int32)
+            esz = 8 if dt == 0 else 4
+            v = self._h_views[name] = arr[off // esz: off // esz + cnt * st: st]
+        return v
+
+    def _scal(self, name) -> float:
+        from ..engine import SCAL_INDEX
+        return float(self._field("scal")[SCAL_INDEX[name]])
 
     def _get_obs(self):
         """cats.py:466-481 (Cats) / 655-671 (CatsLog), from the current state."""
@@ -195,7 +235,7 @@ class Cats:
         if self.n_agents == 0:
             return out
         yp, yd, p = self._field("c_Y_prev"), self._field("c_Yd"), self._field("c_P")
-        ap = float(self._engine.scalar("price")[0])
+        ap = self._scal("price")
         for i in range(self.n_agents):
             out.append(self._make_obs(float(yp[i]), float(yd[i]), float(p[i]), ap))
         return out
@@ -215,8 +255,7 @@ class Cats:
         if self.info_level == 0:
             return {}
         n = self.n_agents
-        eng = self._engine
-        sc = eng.field("scal")[0].cpu().numpy()
+        sc = self._field("scal")
         from ..engine import SCAL_INDEX as S
         Q = self._field("c_Q")
         info = {

@@ -49,6 +49,7 @@ extern "C" {
 /* per-economy status bits (replace the reference's warnings.warn, cats.py:518,535) */
 #define CATS_STATUS_DEPVAL_DIV0 1u
 #define CATS_STATUS_PROFIT_NAN 2u
+#define CATS_STATUS_Z_MISMATCH 4u   /* cats_step_args.z_all was set but this economy's parameters disagree: its results are invalid */
 
 /* columns of the per-period statistics row (the aggregates Cats._get_info reads, cats.py:567-607) */
 enum cats_stat {
@@ -128,6 +129,10 @@ typedef struct cats_step_args {
     void *stream;
     const uint8_t *d_active;    /* DEVICE [B] or NULL: economies with a zero entry sit this call out (state
                                    and outputs untouched); NULL = all.  See cats_reset_masked(). */
+    int32_t z_all[3];           /* z_c, z_k, z_e when EVERY economy of the call has exactly these values; zeros =
+                                   unknown or mixed.  Only a hint for picking a kernel instantiation (the reference's
+                                   defaults 5, 2, 5 at the default size have one with the lists unrolled); an economy
+                                   that disagrees gets CATS_STATUS_Z_MISMATCH. */
 } cats_step_args;
 
 /* Replaces the 26 ABCredit calls of one Cats.step (cats.py:355-413) plus _implement_action,
@@ -208,7 +213,7 @@ void cats_debug_set_group(int economies_per_block);
 
 /* Debug aid: economies of the reference's default size (W=1000, F=100, N=20) with all z <= 5 run a
  * kernel instantiation whose state layout is a compile-time constant (addresses are base + immediate,
- * loop bounds are known: ~18 % fewer instructions).  0 makes later cats_step calls use the generic
+ * loop bounds are known: ~20 % fewer instructions; it also needs z_all == {5, 2, 5}).  0 makes later cats_step calls use the generic
  * kernel for them too; 1 (default) restores the specialisation.  Results never depend on it. */
 void cats_debug_set_static(int on);
 

@@ -20,7 +20,7 @@ N_STATS = 16
 MAX_Z = 8
 
 FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS = 1, 2, 4, 8
-STATUS_DEPVAL_DIV0, STATUS_PROFIT_NAN = 1, 2
+STATUS_DEPVAL_DIV0, STATUS_PROFIT_NAN, STATUS_Z_MISMATCH = 1, 2, 4
 OK, EINVAL, ECUDA, ESMEM = 0, -1, -2, -3
 
 STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_tot", "gdp_deflator",
@@ -51,7 +51,7 @@ class StepArgs(C.Structure):
         ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p), ("d_status", C.c_void_p),
         ("d_stats", C.c_void_p), ("d_tape", C.c_void_p), ("tape_z", C.c_int32 * 3),
         ("max_z", C.c_int32), ("stop_phase", C.c_int32), ("d_debug", C.c_void_p), ("stream", C.c_void_p),
-        ("d_active", C.c_void_p),
+        ("d_active", C.c_void_p), ("z_all", C.c_int32 * 3),
     ]
 
 

@@ -156,11 +156,12 @@ static bool is_default_size(const Layout &L)
     return !off && g_static && L.W == DefaultLayout::kW && L.F == DefaultLayout::kF && L.N == DefaultLayout::kN && smem_pad() == 0;
 }
 // production: Philox draws, no debug stop, no debug image
-static KernelFn select_kernel(const Layout &L, int max_z, int g, bool masked = false, bool production = true)
+static KernelFn select_kernel(const Layout &L, int max_z, int g, bool masked = false, bool production = true,
+                              bool default_z = false)
 {
     if (masked) return kernel_masked(g);   // resets are rare: one instantiation serves every size and z
     if (!production) return kernel_debug(max_z, g);
-    if (max_z > 0 && max_z <= 5 && is_default_size(L)) return kernel_static(g);
+    if (default_z && is_default_size(L)) return kernel_static(g);
     return kernel_prod(max_z, g);
 }
 static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 15) & ~15; }
@@ -351,7 +352,7 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int g = choose_group(L, 1ll << 40, nsm);   // the shape of a launch that fills the GPU
-    if (int rc = configure_kernel(L, select_kernel(L, 5, g), g, &occ, &sms)) return rc;
+    if (int rc = configure_kernel(L, select_kernel(L, 5, g, false, true, true), g, &occ, &sms)) return rc;
     if (threads) *threads = kThreads * g;            // per block: g economies, one warp each
     if (smem_bytes) *smem_bytes = slice_bytes(L) * g;
     if (blocks_per_sm) *blocks_per_sm = occ;
@@ -437,7 +438,8 @@ int cats_step(const cats_step_args *s)
     const int g = choose_group(a.L, s->B, nsm);
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
-    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, !s->d_tape && !s->stop_phase && !s->d_debug);
+    const bool default_z = s->z_all[0] == DefaultLayout::kZc && s->z_all[1] == DefaultLayout::kZk && s->z_all[2] == DefaultLayout::kZe;
+    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, !s->d_tape && !s->stop_phase && !s->d_debug, default_z);
     if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
     fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
     g_launches++;

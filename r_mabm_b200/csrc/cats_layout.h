@@ -127,11 +127,12 @@ constexpr Layout make_layout(int W, int F, int N)
 
 
 // The reference's default economy (W=1000, F=100, N=20: cats.py:115-117, every BASELINE configuration
-// but the 10x one) with the layout resolved at compile time: the same member names as `Layout`, as
+// but the 10x one; candidate-list lengths z_c=5, z_k=2, z_e=5) with the layout resolved at compile time: the same member names as `Layout`, as
 // static constants, so that `L.F`, `L.o_c`, ... in the phase code fold into immediates (addresses
 // become base + immediate, loops get constant bounds).
 struct DefaultLayout {
     static constexpr int kW = 1000, kF = 100, kN = 20;
+    static constexpr int kZc = 5, kZk = 2, kZe = 5;   // the default z_c, z_k, z_e (cats.py:70-72)
     static constexpr Layout k = make_layout(kW, kF, kN);
     static constexpr int32_t W = k.W;
     static constexpr int32_t F = k.F;

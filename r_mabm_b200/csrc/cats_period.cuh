@@ -80,7 +80,8 @@ template <> struct LastPhase<true> {
 };
 // MODE 0: every feature (replay tape, debug stop after a phase, debug image of the working set).
 // MODE 1: production -- draws come from Philox only, no debug stop, no debug image.
-// MODE 2: production for the default size -- the layout is a compile-time constant (DefaultLayout) too.
+// MODE 2: production for the reference's default configuration -- the layout (W=1000, F=100, N=20) and
+//         the candidate-list lengths (z_c=5, z_k=2, z_e=5) are compile-time constants (DefaultLayout) too.
 template <int MODE>
 struct CtxT {
     static constexpr bool kStatic = MODE == 2;   // layout resolved at compile time
@@ -111,9 +112,10 @@ struct CtxT {
     __device__ __forceinline__ double2 *hh() const { return reinterpret_cast<double2 *>(blob + layout().o_PA); }
     __device__ __forceinline__ double &PA(int h) const { return hh()[h].x; }
     __device__ __forceinline__ double &perm(int h) const { return hh()[h].y; }
-    __device__ __forceinline__ int z_c() const { return (int)par()[P_z_c]; }
-    __device__ __forceinline__ int z_k() const { return (int)par()[P_z_k]; }
-    __device__ __forceinline__ int z_e() const { return (int)par()[P_z_e]; }
+    // candidate-list lengths: constants in the default-configuration instantiation (the host checks them)
+    __device__ __forceinline__ int z_c() const { if constexpr (kStatic) return DefaultLayout::kZc; else return (int)par()[P_z_c]; }
+    __device__ __forceinline__ int z_k() const { if constexpr (kStatic) return DefaultLayout::kZk; else return (int)par()[P_z_k]; }
+    __device__ __forceinline__ int z_e() const { if constexpr (kStatic) return DefaultLayout::kZe; else return (int)par()[P_z_e]; }
     __device__ __forceinline__ double *cf(int field) const { return reinterpret_cast<double *>(blob + layout().o_c + field * layout().rowF); }  // GLOBAL
     // K-firm rows: hot ones (P, Yd, Q) are SHARED, the others GLOBAL; `field` is a compile-time constant
     __device__ __forceinline__ double *kf(int field) const
@@ -1376,10 +1378,13 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
         // market need (employment links, firm rows) into L2 now, household wealth before the goods market
         bulk_prefetch_l2(blob + L.o_Oc, (uint32_t)(L.o_PA - L.o_Oc));
     }
+    bool bad_z = false;
     // parameters (shared row or per-economy row) while the copy is in flight
     const double *pr = a.params + (a.params_stride ? (size_t)b * (size_t)a.params_stride : 0);
     for (int i = c.lane; i < N_PARAMS; i += 32) c.par()[i] = pr[i];
     if (c.lane == 0) c.par()[P_log1mtheta] = det_log(1.0 - pr[P_theta]);
+    if (ST && c.lane == 0 && ((int)pr[P_z_c] != DefaultLayout::kZc || (int)pr[P_z_k] != DefaultLayout::kZk || (int)pr[P_z_e] != DefaultLayout::kZe))
+        bad_z = true;      // the call declared the default z for every economy and this one disagrees
     // every transient is written before it is read within a period; only a debug image of a period
     // stopped half-way shows the ones not reached yet, and those must read as zero
     if (!PROD && a.debug)
@@ -1436,7 +1441,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     }
     if (c.lane == 0) {
         if (a.terminated) a.terminated[b] = c.scal()[S_terminated] != 0.0 ? 1 : 0;
-        if (a.status) a.status[b] = (unsigned)c.scal()[S_status];
+        if (a.status) a.status[b] = (unsigned)c.scal()[S_status] | (bad_z ? CATS_STATUS_Z_MISMATCH : 0u);
     }
     if (!PROD && a.debug) {
         // transients image (cats_workset_field_info): Ld vac cFtot cKdem cYstock cvalinv kFtot kYstock

@@ -179,6 +179,8 @@ class BatchedCats:
             a.d_tape = tape.data_ptr()
             a.tape_z[0], a.tape_z[1], a.tape_z[2] = self._z
         a.max_z = self._max_z
+        if self._z is not None:
+            a.z_all[0], a.z_all[1], a.z_all[2] = self._z
         a.stop_phase = stop_phase
         a.d_debug = debug.data_ptr() if debug is not None else None
         a.stream = self._stream()

@@ -131,3 +131,29 @@ def test_static_layout_kernel_equals_the_generic_kernel_at_the_default_size():
                     assert torch.equal(a, b), f"static={static} group={g}"
     finally:
         lib.cats_debug_set_static(1); lib.cats_debug_set_group(0)
+
+
+def test_default_size_with_other_z_takes_the_generic_kernel_and_a_false_hint_is_flagged():
+    """The default-configuration kernel has z_c, z_k, z_e = 5, 2, 5 compiled in.  Other values at the
+    default size run the generic production kernel (checked against the oracle); a call that declares
+    the defaults while an economy's parameters say otherwise gets CATS_STATUS_Z_MISMATCH."""
+    import ctypes as C
+    from r_mabm_b200 import _native as nat
+    from r_mabm_b200.engine import BatchedCats
+    from oracle import oracle as orc
+    from parity_util import compare_state
+    p = {"z_c": 4, "z_k": 3, "z_e": 2}
+    env = BatchedCats(3, params=dict(p), seed=5)
+    env.run(6)
+    torch.cuda.synchronize()
+    refs = [orc.OracleEconomy(1000, 100, 20, params=dict(p), seed=5, economy=b) for b in range(3)]
+    for o in refs:
+        for _ in range(6):
+            o.step()
+    assert compare_state(env, refs, "z = 4, 3, 2") == []
+    assert int(env._status.max()) == 0
+    a = env._args(1, env.flags | nat.FLAG_BURNIN, want_io=False)
+    a.z_all[0], a.z_all[1], a.z_all[2] = 5, 2, 5            # a lie
+    nat.check(env._lib.cats_step(C.byref(a)))
+    torch.cuda.synchronize()
+    assert (env._status.cpu().numpy() & nat.STATUS_Z_MISMATCH).all()

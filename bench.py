@@ -227,8 +227,9 @@ def run_b200(args):
     env.run(args.burnin)                                   # the reference's reset(): t_burnin periods
     actions = torch.ones((B, 1, 2), dtype=torch.float64, device=dev)
     mask = torch.zeros((B, 1), dtype=torch.uint8, device=dev)     # "dummy" agent: heuristic decision kept
-    h_actions = torch.ones((B, 1, 2), dtype=torch.float64).pin_memory()
-    h_mask = torch.zeros((B, 1), dtype=torch.uint8).pin_memory()
+    # pinned host buffers the caller fills: the engine's staging block (one H2D and one D2H copy per step)
+    h_actions, h_mask = env.host_action_buffers()
+    h_actions.fill_(1.0); h_mask.zero_()
     lib = nat.load()
 
     # ---- device-resident arm ----

@@ -143,6 +143,10 @@ int cats_step(const cats_step_args *args);
  * actions host->device, runs the step, copies the outputs back and synchronises the stream.
  * d_scratch must hold cats_host_scratch_bytes(B, n_agents, n_periods) device bytes. */
 size_t cats_host_scratch_bytes(int64_t B, int n_agents, int n_periods);
+/* Byte offsets of the seven sections of that staging block (actions, mask, obs, reward, terminated,
+ * status, stats).  A caller whose HOST buffers sit at the same offsets inside one (pinned) block gets a
+ * single copy in each direction from cats_step_host instead of one per buffer. */
+int cats_host_block_offsets(int64_t B, int n_agents, int n_periods, uint64_t out7[7]);
 int cats_step_host(const cats_step_args *args_with_host_io, void *d_scratch);
 
 /* ---- learned firms: tabular Q-learning policy, one table per (economy, agent) --------------------

@@ -479,18 +479,31 @@ int cats_q_step(const cats_q_args *s)
     return CATS_OK;
 }
 
+// sections of the staging block: actions | mask | obs | reward | terminated | status | stats, each 256-byte aligned
+static void host_block_layout(int64_t B, int n_agents, int n_periods, size_t off[8])
+{
+    const size_t nA = (size_t)(n_agents > 0 ? n_agents : 0), b = (size_t)(B > 0 ? B : 0);
+    const size_t np = (size_t)(n_periods > 0 ? n_periods : 1);
+    const size_t sz[7] = {b * nA * 16, b * nA, b * nA * 16, b * nA * 8, b, b * 4, b * np * N_STATS * 8};
+    size_t o = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = o; o += (sz[i] + 255) & ~(size_t)255; }
+    off[7] = o;
+}
+
 size_t cats_host_scratch_bytes(int64_t B, int n_agents, int n_periods)
 {
-    size_t nA = (size_t)(n_agents > 0 ? n_agents : 0), b = (size_t)(B > 0 ? B : 0);
-    size_t o = 0;
-    o += (b * nA * 2 * 8 + 255) & ~(size_t)255;  // actions
-    o += (b * nA + 255) & ~(size_t)255;          // mask
-    o += (b * nA * 2 * 8 + 255) & ~(size_t)255;  // obs
-    o += (b * nA * 8 + 255) & ~(size_t)255;      // reward
-    o += (b + 255) & ~(size_t)255;               // terminated
-    o += (b * 4 + 255) & ~(size_t)255;           // status
-    o += (b * (size_t)(n_periods > 0 ? n_periods : 1) * N_STATS * 8 + 255) & ~(size_t)255;  // stats
-    return o;
+    size_t off[8];
+    host_block_layout(B, n_agents, n_periods, off);
+    return off[7];
+}
+
+int cats_host_block_offsets(int64_t B, int n_agents, int n_periods, uint64_t out7[7])
+{
+    if (!out7) return fail(CATS_EINVAL, "null argument%s", "");
+    size_t off[8];
+    host_block_layout(B, n_agents, n_periods, off);
+    for (int i = 0; i < 7; ++i) out7[i] = off[i];
+    return CATS_OK;
 }
 
 int cats_step_host(const cats_step_args *h, void *d_scratch)
@@ -499,31 +512,57 @@ int cats_step_host(const cats_step_args *h, void *d_scratch)
     cudaStream_t st = (cudaStream_t)h->stream;
     const size_t nA = (size_t)(h->n_agents > 0 ? h->n_agents : 0), b = (size_t)(h->B > 0 ? h->B : 0);
     const size_t np = (size_t)(h->n_periods > 0 ? h->n_periods : 1);
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    unsigned char *p = (unsigned char *)d_scratch;
-    double *d_act = (double *)p; p += up(b * nA * 16);
-    unsigned char *d_msk = p; p += up(b * nA);
-    double *d_obs = (double *)p; p += up(b * nA * 16);
-    double *d_rew = (double *)p; p += up(b * nA * 8);
-    unsigned char *d_term = p; p += up(b);
-    unsigned *d_stat = (unsigned *)p; p += up(b * 4);
-    double *d_stats = (double *)p;
+    size_t off[8];
+    host_block_layout(h->B, h->n_agents, h->n_periods, off);
+    unsigned char *base = (unsigned char *)d_scratch;
+    double *d_act = (double *)(base + off[0]);
+    unsigned char *d_msk = base + off[1];
+    double *d_obs = (double *)(base + off[2]);
+    double *d_rew = (double *)(base + off[3]);
+    unsigned char *d_term = base + off[4];
+    unsigned *d_stat = (unsigned *)(base + off[5]);
+    double *d_stats = (double *)(base + off[6]);
     cats_step_args s = *h;
     cudaError_t e = cudaSuccess;
-    if (h->d_actions && nA) { e = cudaMemcpyAsync(d_act, h->d_actions, b * nA * 16, cudaMemcpyHostToDevice, st); s.d_actions = d_act; }
-    if (e == cudaSuccess && h->d_action_mask && nA) { e = cudaMemcpyAsync(d_msk, h->d_action_mask, b * nA, cudaMemcpyHostToDevice, st); s.d_action_mask = d_msk; }
+    const bool up_act = h->d_actions && nA, up_msk = h->d_action_mask && nA;
+    // A caller that lays its host buffers out like the staging block (cats_host_block_offsets) gets one copy
+    // in each direction instead of one per buffer.
+    if (up_act && up_msk &&
+        (const unsigned char *)h->d_action_mask - (const unsigned char *)h->d_actions == (ptrdiff_t)(off[1] - off[0])) {
+        e = cudaMemcpyAsync(d_act, h->d_actions, (off[1] - off[0]) + b * nA, cudaMemcpyHostToDevice, st);
+    } else {
+        if (up_act) e = cudaMemcpyAsync(d_act, h->d_actions, b * nA * 16, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && up_msk) e = cudaMemcpyAsync(d_msk, h->d_action_mask, b * nA, cudaMemcpyHostToDevice, st);
+    }
     if (e != cudaSuccess) return fail(CATS_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+    if (up_act) s.d_actions = d_act;
+    if (up_msk) s.d_action_mask = d_msk;
     s.d_obs = (h->d_obs && nA) ? d_obs : nullptr;
     s.d_reward = (h->d_reward && nA) ? d_rew : nullptr;
     s.d_terminated = h->d_terminated ? d_term : nullptr;
     s.d_status = h->d_status ? d_stat : nullptr;
     s.d_stats = h->d_stats ? d_stats : nullptr;
     if (int rc = cats_step(&s)) return rc;
-    if (s.d_obs) e = cudaMemcpyAsync(h->d_obs, d_obs, b * nA * 16, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && s.d_reward) e = cudaMemcpyAsync(h->d_reward, d_rew, b * nA * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && s.d_terminated) e = cudaMemcpyAsync(h->d_terminated, d_term, b, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && s.d_status) e = cudaMemcpyAsync(h->d_status, d_stat, b * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && s.d_stats) e = cudaMemcpyAsync(h->d_stats, d_stats, b * np * N_STATS * 8, cudaMemcpyDeviceToHost, st);
+    // outputs: {host pointer, section, bytes}
+    struct Out { void *host; int sec; size_t bytes; } outs[5] = {
+        {s.d_obs ? (void *)h->d_obs : nullptr, 2, b * nA * 16}, {s.d_reward ? (void *)h->d_reward : nullptr, 3, b * nA * 8},
+        {s.d_terminated ? (void *)h->d_terminated : nullptr, 4, b}, {s.d_status ? (void *)h->d_status : nullptr, 5, b * 4},
+        {s.d_stats ? (void *)h->d_stats : nullptr, 6, b * np * N_STATS * 8}};
+    int first = -1, last = -1; bool mirrored = true;
+    for (int i = 0; i < 5; ++i) {
+        if (!outs[i].host) continue;
+        if (first < 0) first = i;
+        last = i;
+        if ((unsigned char *)outs[i].host - (unsigned char *)outs[first].host != (ptrdiff_t)(off[outs[i].sec] - off[outs[first].sec]))
+            mirrored = false;
+    }
+    if (first >= 0 && mirrored && first != last) {
+        e = cudaMemcpyAsync(outs[first].host, base + off[outs[first].sec],
+                            (off[outs[last].sec] - off[outs[first].sec]) + outs[last].bytes, cudaMemcpyDeviceToHost, st);
+    } else {
+        for (int i = 0; i < 5 && e == cudaSuccess; ++i)
+            if (outs[i].host) e = cudaMemcpyAsync(outs[i].host, base + off[outs[i].sec], outs[i].bytes, cudaMemcpyDeviceToHost, st);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "D2H copy / sync: %s", cudaGetErrorString(e));
     return CATS_OK;

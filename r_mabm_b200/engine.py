@@ -271,27 +271,52 @@ class BatchedCats:
             self._obs[:, :nA] = torch.where(m, new, self._obs[:, :nA])
         return self._obs[:, :nA]
 
+    def _ensure_host_block(self) -> None:
+        nA, B = self.n_agents, self.B
+        need = int(self._lib.cats_host_scratch_bytes(B, nA, 1))
+        if self._host_scratch is None or self._host_scratch.numel() < need:
+            self._host_scratch = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            # ONE pinned block laid out like the device staging block: the library then moves the inputs
+            # with one copy and the outputs with one copy (cats_host_block_offsets)
+            off = (C.c_uint64 * 7)()
+            nat.check(self._lib.cats_host_block_offsets(B, nA, 1, off))
+            off = [int(x) for x in off]
+            blk = self._host_block = torch.empty((need,), dtype=torch.uint8).pin_memory()
+            A1 = max(nA, 1)
+
+            def view(o, nbytes, dtype, shape):
+                return blk[o:o + nbytes].view(dtype).view(shape)
+            self._h_act_in = view(off[0], B * nA * 16, torch.float64, (B, nA, 2)) if nA else None
+            self._h_mask_in = view(off[1], B * nA, torch.uint8, (B, nA)) if nA else None
+            self._h_obs = view(off[2], B * nA * 16, torch.float64, (B, nA, 2)) if nA else torch.empty((B, A1, 2), dtype=torch.float64)
+            self._h_rew = view(off[3], B * nA * 8, torch.float64, (B, nA)) if nA else torch.empty((B, A1), dtype=torch.float64)
+            self._h_term = view(off[4], B, torch.uint8, (B,))
+            self._h_status = view(off[5], B * 4, torch.int32, (B,))
+            self._h_stats = view(off[6], B * nat.N_STATS * 8, torch.float64, (B, 1, nat.N_STATS))
+
     def step_host(self, actions_host: torch.Tensor | None, mask_host: torch.Tensor | None = None,
                   want_stats: bool = True):
         """End-to-end step with HOST buffers (pinned recommended): host->device copy of the
         actions, the period kernel, device->host copy of obs / reward / terminated / stats, one
         stream sync.  This is the call bench.py times for `e2e`."""
         nA, B = self.n_agents, self.B
-        need = int(self._lib.cats_host_scratch_bytes(B, nA, 1))
-        if self._host_scratch is None or self._host_scratch.numel() < need:
-            self._host_scratch = torch.empty((need,), dtype=torch.uint8, device=self.device)
-            self._h_obs = torch.empty((B, max(nA, 1), 2), dtype=torch.float64).pin_memory()
-            self._h_rew = torch.empty((B, max(nA, 1)), dtype=torch.float64).pin_memory()
-            self._h_term = torch.empty((B,), dtype=torch.uint8).pin_memory()
-            self._h_status = torch.empty((B,), dtype=torch.int32).pin_memory()
-            self._h_stats = torch.empty((B, 1, nat.N_STATS), dtype=torch.float64).pin_memory()
+        self._ensure_host_block()
         a = self._args(1, self.flags if nA > 0 and actions_host is not None else self.flags | nat.FLAG_BURNIN,
                        want_io=False)
         if nA > 0 and actions_host is not None:
             if tuple(actions_host.shape) != (B, nA, 2) or actions_host.dtype != torch.float64 or actions_host.is_cuda:
                 raise ValueError("actions_host must be a float64 CPU tensor of shape [B, n_agents, 2]")
-            a.d_actions = actions_host.data_ptr()
-            a.d_action_mask = mask_host.data_ptr() if mask_host is not None else None
+            # staged through the pinned block (a host-to-host copy of a few hundred KB) unless the caller
+            # already wrote into the block's own views (`host_action_buffers`)
+            if actions_host.data_ptr() != self._h_act_in.data_ptr():
+                self._h_act_in.copy_(actions_host)
+            a.d_actions = self._h_act_in.data_ptr()
+            if mask_host is not None:
+                if mask_host.data_ptr() != self._h_mask_in.data_ptr():
+                    self._h_mask_in.copy_(mask_host)
+                a.d_action_mask = self._h_mask_in.data_ptr()
+            else:
+                a.d_action_mask = None
             a.d_obs = self._h_obs.data_ptr(); a.d_reward = self._h_rew.data_ptr()
         a.d_terminated = self._h_term.data_ptr(); a.d_status = self._h_status.data_ptr()
         a.d_stats = self._h_stats.data_ptr() if want_stats else None
@@ -299,6 +324,12 @@ class BatchedCats:
             nat.check(self._lib.cats_step_host(C.byref(a), self._host_scratch.data_ptr()))
         self.periods_done += 1
         return self._h_obs[:, :nA], self._h_rew[:, :nA], self._h_term, (self._h_stats if want_stats else None)
+
+    def host_action_buffers(self):
+        """Pinned host views [B, n_agents, 2] float64 and [B, n_agents] uint8 inside the staging block:
+        fill these and pass them to `step_host` to skip the host-side staging copy."""
+        self._ensure_host_block()
+        return self._h_act_in, self._h_mask_in
 
     def h2d_bytes_per_step(self) -> int:
         return self.B * self.n_agents * 2 * 8

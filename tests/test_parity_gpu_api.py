@@ -162,6 +162,25 @@ def test_step_host_equals_device_step():
         assert torch.equal(ho, do.cpu()) and torch.equal(hr, dr.cpu()) and torch.equal(ht, dt.cpu())
         assert torch.equal(hs, ds.cpu())
     assert torch.equal(a.blobs, b.blobs)
+    # the caller's own buffers (not laid out like the staging block): one copy per buffer, same results;
+    # and the block's own input views, filled in place
+    import ctypes as C
+    from r_mabm_b200 import _native as nat
+    h_obs = torch.empty((B, A, 2), dtype=torch.float64).pin_memory()
+    h_rew = torch.empty((B, A), dtype=torch.float64).pin_memory()
+    h_term = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    h_stats = torch.empty((B, 1, nat.N_STATS), dtype=torch.float64).pin_memory()
+    args = a._args(1, a.flags, want_io=False)
+    pa, pm = acts.pin_memory(), mask.pin_memory()
+    args.d_actions, args.d_action_mask = pa.data_ptr(), pm.data_ptr()
+    args.d_obs, args.d_reward, args.d_terminated = h_obs.data_ptr(), h_rew.data_ptr(), h_term.data_ptr()
+    args.d_status, args.d_stats = None, h_stats.data_ptr()
+    nat.check(a._lib.cats_step_host(C.byref(args), a._host_scratch.data_ptr()))
+    ia, im = b.host_action_buffers()
+    ia.copy_(acts); im.copy_(mask)
+    ho, hr, ht, hs = b.step_host(ia, im, want_stats=True)
+    assert torch.equal(h_obs, ho) and torch.equal(h_rew, hr) and torch.equal(h_term, ht) and torch.equal(h_stats, hs)
+    assert torch.equal(a.blobs, b.blobs)
 
 
 def test_full_size_invariants_1024_economies():

@@ -188,3 +188,75 @@ def test_active_mask_leaves_the_other_economies_untouched():
     for b in idle:
         assert torch.equal(env.blobs[b], before[b]) and float(stats[b].abs().sum()) == 0.0
     assert float(stats[0, -1, 2]) == refs[0].scal("Un")
+
+
+def _invariants(env, stats=None):
+    """Properties every faithful CATS state has (docs/MODEL.md section 6), on the whole batch."""
+    B, F, N = env.B, env.F, env.N
+    Oc = env.field("Oc")
+    emp = (Oc >= 0)
+    counts = torch.zeros((B, F + N), dtype=torch.int64, device="cuda")
+    counts.scatter_add_(1, Oc.clamp(min=0).long(), emp.long())
+    leff = torch.cat([env.field("c_Leff"), env.field("k_Leff")], 1).long()
+    assert torch.equal(counts, leff)                                    # employment links == head-counts
+    Q, Y = env.field("c_Q"), env.field("c_Y_prev")
+    assert ((Q >= 0) & (Q <= Y * (1 + 1e-12) + 1e-12)).all()            # sales within production
+    assert (env.field("PA") >= -1e-9).all() and (env.field("c_deb") >= 0).all() and (env.field("k_deb") >= 0).all()
+    assert (env.field("c_P") > 0).all() and (env.field("k_P") > 0).all()
+    assert torch.isfinite(env.field("scal")).all()
+    # Un is taken by update_tracking_variables! BEFORE firms_go_bankrupt! releases the workers of the
+    # firms that exit (cats.py:401-404): it can only be below the end-of-period share of unemployed
+    un = env.scalar("Un")
+    assert ((un >= 0) & (un <= 1.0 - emp.sum(1).double() / env.W + 1e-12)).all()
+    if stats is not None:
+        assert torch.isfinite(stats).all()
+
+
+def test_config3_bench_width_16384_economies_invariants_and_sampled_parity():
+    """BASELINE.json config 3 at the width bench.py runs (16,384 default-size economies on one GPU, the
+    production kernel): invariants on every economy after the burn-in and 20 more periods, and a sample
+    of economies spread over the batch bit-identical to the oracle after the same 320 periods."""
+    B, T = 16384, 320
+    env = _env(B, seed=20260119)
+    env.run(300)
+    stats = env.run(20, want_stats=True)
+    torch.cuda.synchronize()
+    _invariants(env, stats)
+    ids = [0, 13, 14, 4143, 4144, 8191, 12345, 16383]          # block and wave boundaries included
+    refs = [orc.OracleEconomy(1000, 100, 20, seed=20260119, economy=i) for i in ids]
+    stats_ref = orc.run_batch(refs, T, n_threads=min(len(ids), os.cpu_count() or 1), want_stats=True)
+    assert np.array_equal(bits(stats[ids].cpu().numpy()), bits(stats_ref[:, 300:]))
+
+    class Sub:
+        W, F, N = env.W, env.F, env.N
+
+        @staticmethod
+        def field(name):
+            return env.field(name)[ids]
+    assert compare_state(Sub, refs, "t=320") == []
+    # Monte-Carlo seeds are different economies, and the batch does not care how it is split
+    assert len({float(x) for x in stats[:, -1, 0].cpu()}) > 16000
+    half = _env(8192, seed=20260119, economy_base=8192)
+    half.run(300); half.run(20)
+    torch.cuda.synchronize()
+    assert torch.equal(half.blobs, env.blobs[8192:])
+
+
+def test_config5_full_width_256_scaled_economies():
+    """BASELINE.json config 5 at full width: 256 economies of 10x size.  Invariants on all of them, two of
+    them against the oracle."""
+    B, W, F, N, T = 256, 10000, 1000, 200, 12
+    env = _env(B, W=W, F=F, N=N, seed=5)
+    stats = env.run(T, want_stats=True)
+    torch.cuda.synchronize()
+    _invariants(env, stats)
+    ids = [0, 255]
+    refs = [orc.OracleEconomy(W, F, N, seed=5, economy=i) for i in ids]
+    stats_ref = orc.run_batch(refs, T, n_threads=2, want_stats=True)
+    assert np.array_equal(bits(stats[ids].cpu().numpy()), bits(stats_ref))
+
+    class Sub:
+        pass
+    Sub.W, Sub.F, Sub.N = W, F, N
+    Sub.field = staticmethod(lambda name: env.field(name)[ids])
+    assert compare_state(Sub, refs, f"t={T}") == []

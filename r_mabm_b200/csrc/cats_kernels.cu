@@ -79,8 +79,8 @@ __device__ __forceinline__ int q_bin(double x, double lo, double step, int n)
 // (max value, first index of it) over row[0, m): lanes stride, then a butterfly on (value, index)
 __device__ __forceinline__ void q_row_max(const double *row, int m, int lane, double &best, int &arg)
 {
-    best = -__longlong_as_double(0x7ff0000000000000LL) * 1.0; arg = 0x7fffffff;
-    best = __longlong_as_double(0xfff0000000000000LL);
+    best = __longlong_as_double(0xfff0000000000000LL);   // -inf
+    arg = 0x7fffffff;
     for (int i = lane; i < m; i += 32) {
         const double v = row[i];
         if (v > best || (v == best && i < arg)) { best = v; arg = i; }

@@ -132,3 +132,26 @@ def test_fused_update_is_the_scalar_qlearner_rule_and_masks_work():
                 assert (q1[b, a] != q0[b, a]).sum() <= 1
             else:
                 assert np.array_equal(q1[b, a], q0[b, a])
+
+
+def test_fused_rollout_does_not_depend_on_sharding():
+    """Economies 0..5 as one batch, and as two shards with `economy_base` (what two ranks would run): same
+    actions, rewards and Q tables -- env draws and exploration draws are keyed by the global economy id."""
+    from r_mabm_b200.engine import BatchedCats
+    from r_mabm_b200.environments import CatsLog
+    from r_mabm_b200.rollout import BatchedRollout, FusedQPolicy
+    bounds = dict(CatsLog._default_gym_spaces_bounds)
+
+    def run(B, base):
+        env = BatchedCats(B, W=300, F=30, N=6, n_agents=2, log_mode=True, seed=4, economy_base=base)
+        pol = FusedQPolicy(B, 2, bounds, n_bins=(5, 5, 3, 3), epsilon=0.5, seed=9, economy_base=base)
+        ro = BatchedRollout(env, pol, t_burnin=10, T=100)
+        ro.reset(seed=4)
+        rewards = torch.stack([ro.step(train=True)[0].clone() for _ in range(15)])
+        torch.cuda.synchronize()
+        return rewards.cpu(), pol.Q.cpu(), env.blobs.cpu()
+    full = run(6, 0)
+    lo, hi = run(2, 0), run(4, 2)
+    assert torch.equal(full[0], torch.cat([lo[0], hi[0]], 1))
+    assert torch.equal(full[1], torch.cat([lo[1], hi[1]], 0))
+    assert torch.equal(full[2], torch.cat([lo[2], hi[2]], 0))

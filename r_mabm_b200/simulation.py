@@ -1,6 +1,10 @@
-"""`Simulation`: episode driver with the interface of rmabm.Simulation
-(/root/reference/rmabm/simulation.py:12-207): `step`, `run_episode`, `train_agents`, `reset`,
-`init_logger`, `*_history` properties, epsilon schedule max(0.01, 0.9 ** episode).
+"""`Simulation`: the episode driver behind the reference's examples, over this framework's `Cats`.
+
+Interface of rmabm.Simulation (/root/reference/rmabm/simulation.py:12-207): constructor arguments,
+`step` / `run_episode` / `train_agents` / `reset` / `init_logger`, the `*_history` properties, the
+epsilon schedule max(0.01, 0.9 ** episode) -- so `examples/heuristic_run.py` and
+`examples/agent_training.py` run unchanged.  Thousands of economies at once go through
+`r_mabm_b200.rollout.BatchedRollout` instead; this class is the one-economy, host-side loop.
 """
 from __future__ import annotations
 
@@ -9,84 +13,101 @@ from typing import Any, Callable
 
 import numpy as np
 
-from .agents import Dummy, QLearner
+from .agents import QLearner
 from .logger import Logger
+
+
+class _Trace:
+    """What one episode leaves behind: a row per step of (observations, actions, rewards, info)."""
+
+    __slots__ = ("obs", "act", "reward", "info")
+
+    def __init__(self):
+        self.obs, self.act, self.reward, self.info = [], [], [], []
+
+    def add(self, obs, act, reward, info) -> None:
+        self.obs.append(obs)
+        self.act.append(act)
+        self.reward.append(reward)
+        self.info.append(info)
+
+    def write(self, logger: Logger, episode: int) -> None:
+        # the files rmabm.Logger users read: ep{n}_obs, ep{n}_act, ep{n}_rewards, ep{n}_{info key}
+        logger.log_obs(self.obs, episode)
+        logger.log_act(self.act, episode)
+        logger.log_array(np.array(self.reward), f"ep{episode}_rewards")
+        logger.log_info(self.info, episode)
 
 
 class Simulation:
     def __init__(self, environment, agents: list, n_episodes: int = 100, current_episode: int = 1):
-        if environment.n_agents != len(agents):
+        if len(agents) != environment.n_agents:
             raise ValueError("Number of agents must match number of agents in the environment.")
-        self.env = environment
-        self.agents = agents
-        self.qlearners = [a for a in agents if isinstance(a, QLearner)]
-        self.n_episodes = n_episodes
-        self.current_episode = current_episode
+        self.env, self.agents = environment, agents
+        self.qlearners = [ag for ag in agents if isinstance(ag, QLearner)]
+        self.n_episodes, self.current_episode = n_episodes, current_episode
         self.logger: Logger | None = None
-        self._clear_histories()
-        self._obs, self._info = self.env.reset()
+        self._begin(*self.env.reset())
+
+    # -- episode state --------------------------------------------------------------------------
+    def _begin(self, obs, info) -> None:
+        self._trace = _Trace()
+        self._obs, self._info = obs, info
         self._next_obs = self._reward = None
         self._terminated = self._truncated = False
 
-    def _clear_histories(self) -> None:
-        self._obs_history, self._act_history, self._reward_history, self._info_history = [], [], [], []
+    @property
+    def _done(self) -> bool:
+        return bool(self._terminated or self._truncated)
 
+    # the reference keeps four parallel lists under these names (simulation.py:60-64); same data here
+    _obs_history = property(lambda self: self._trace.obs)
+    _act_history = property(lambda self: self._trace.act)
+    _reward_history = property(lambda self: self._trace.reward)
+    _info_history = property(lambda self: self._trace.info)
+    obs_history, act_history = _obs_history, _act_history
+    reward_history, info_history = _reward_history, _info_history
+
+    # -- public interface -------------------------------------------------------------------------
     def init_logger(self, log_name: str, log_directory: str | Path, use_timestamp: bool = True) -> None:
         self.logger = Logger(log_name, log_directory, use_timestamp)
 
     def reset(self, seed: int | None = None, options: dict[str, Any] | None = None) -> None:
-        self._obs, self._info = self.env.reset(seed=seed, options=options)
-        self._next_obs = self._reward = None
-        self._terminated = self._truncated = False
-        self._clear_histories()
+        """New model + burn-in in the environment (which also seeds `random` and numpy for the agents)."""
+        self._begin(*self.env.reset(seed=seed, options=options))
 
     def step(self, train: bool = False) -> None:
-        actions = [agent.get_action(obs) for agent, obs in zip(self.agents, self._obs)]
-        self._next_obs, self._reward, self._terminated, self._truncated, self._info = self.env.step(actions)
-        self._obs_history.append(self._obs)
-        self._act_history.append(actions)
-        self._reward_history.append(self._reward)
-        self._info_history.append(self._info)
+        """Agents act on the current observations, the economy advances one period, and -- if asked --
+        every agent learns from its own (observation, reward, next observation)."""
+        seen = self._obs
+        chosen = [ag.get_action(o) for ag, o in zip(self.agents, seen)]
+        self._next_obs, self._reward, self._terminated, self._truncated, self._info = self.env.step(chosen)
+        self._trace.add(seen, chosen, self._reward, self._info)
         if train:
-            for i, agent in enumerate(self.agents):
-                agent.train(self._obs[i], self._reward[i], self._next_obs[i], self._terminated)
+            for k, ag in enumerate(self.agents):
+                ag.train(seen[k], self._reward[k], self._next_obs[k], self._terminated)
         self._obs = self._next_obs
 
     def run_episode(self, train: bool = False) -> None:
-        while not self._terminated and not self._truncated:
+        """Step until the episode terminates or is truncated, write the log (if a logger is set), then
+        reset for the next episode."""
+        while not self._done:
             self.step(train=train)
-        if self.logger:
-            self.logger.log_obs(self._obs_history, self.current_episode)
-            self.logger.log_act(self._act_history, self.current_episode)
-            self.logger.log_array(np.array(self._reward_history), f"ep{self.current_episode}_rewards")
-            self.logger.log_info(self._info_history, self.current_episode)
+        if self.logger is not None:
+            self._trace.write(self.logger, self.current_episode)
         self.reset()
         self.current_episode += 1
 
     def train_agents(self, n_episodes: int | None = None, update: Callable[..., None] | None = None) -> None:
-        n_episodes = n_episodes or (self.n_episodes - self.current_episode + 1)
-        update = update or self._default_update
-        for _ in range(n_episodes):
+        """Training episodes; after each one `update(agent, simulation)` is applied to the Q-learners
+        (default: the reference's exploration schedule)."""
+        todo = n_episodes or (self.n_episodes - self.current_episode + 1)
+        schedule = update or self._default_update
+        for _ in range(todo):
             self.run_episode(train=True)
-            for agent in self.qlearners:
-                update(agent, self)
+            for learner in self.qlearners:
+                schedule(learner, self)
 
     @staticmethod
-    def _default_update(agent: QLearner, simulation) -> None:
+    def _default_update(agent: QLearner, simulation: "Simulation") -> None:
         agent.epsilon = max(0.01, 0.9 ** simulation.current_episode)
-
-    @property
-    def obs_history(self):
-        return self._obs_history
-
-    @property
-    def act_history(self):
-        return self._act_history
-
-    @property
-    def reward_history(self):
-        return self._reward_history
-
-    @property
-    def info_history(self):
-        return self._info_history

@@ -903,7 +903,7 @@ __device__ void phase_goods_market(C &c)
             if (has) ys = mkt.yr[term].x;
             bool sold = false;
             while (__any_sync(FULL, rem != 0u)) {
-                const int src = rem ? __ffs(rem) - 1 : 0;
+                const int src = __ffs(rem) - 1;   // -1 (no peer left) reads lane 31: the value is not used then
                 const double di = __shfl_sync(FULL, d_t, src);
                 if (rem) {
                     rem &= rem - 1;
@@ -913,7 +913,7 @@ __device__ void phase_goods_market(C &c)
             const bool full = has && !sold && ys > d_t;
             const unsigned so = __ballot_sync(FULL, has && !sold && !full);   // lanes that exhaust their seller
             const int s = so ? __ffs(so) - 1 : 31;
-            const unsigned commit = pend & (s >= 31 ? FULL : ((2u << s) - 1u));
+            const unsigned commit = pend & ((2u << s) - 1u);   // lanes 0..s (s == 31: all, 2u << 31 wraps to 0)
             const bool cm = (commit >> lane) & 1u;
             const int xs = __shfl_sync(FULL, term, s);   // the seller exhausted by lane s (if so != 0)
             bool done = false;

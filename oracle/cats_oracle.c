@@ -955,14 +955,26 @@ void ph_accounting_k(Econ *e)
 }
 
 /* a18 Cats._get_reward (cats.py:493-556), evaluated between accounting and tracking */
+/* sum(p[f] * q[f] for f in [lo, hi)) as CPython >= 3.12 adds floats: Neumaier's compensated summation
+ * (Objects/bltinmodule.c, builtin_sum_impl); CPython <= 3.11 added left to right, a few ulp away. */
+static double py_sum(const double *p, const double *q, int lo, int hi)
+{
+    double acc = 0.0, comp = 0.0;
+    for (int f = lo; f < hi; ++f) {
+        double x = p[f] * q[f], t = acc + x;
+        if (fabs(acc) >= fabs(x)) comp = comp + ((acc - t) + x); else comp = comp + ((x - t) + acc);
+        acc = t;
+    }
+    if (comp != 0.0 && isfinite(comp)) acc = acc + comp;
+    return acc;
+}
+
 void ph_reward(Econ *e, int n_agents, unsigned flags, double *reward)
 {
     if (flags & FLAG_REWARD_RMS) {
-        /* cats.py:548-549: Python sum() over RL firms, then over the others, left to right */
-        double tot_rl = 0.0, tot_other = 0.0;
-        for (int f = 0; f < n_agents; ++f) tot_rl = tot_rl + e->c[C_P][f] * e->c[C_Q][f];
-        for (int f = n_agents; f < e->F; ++f) tot_other = tot_other + e->c[C_P][f] * e->c[C_Q][f];
-        double total = tot_rl + tot_other;
+        /* cats.py:548-549: Python's built-in sum() over the RL firms' revenues, then over the others';
+         * the two sums are added plainly.  py_sum below is CPython >= 3.12's float summation. */
+        double total = py_sum(e->c[C_P], e->c[C_Q], 0, n_agents) + py_sum(e->c[C_P], e->c[C_Q], n_agents, e->F);
         for (int a = 0; a < n_agents; ++a) reward[a] = (e->c[C_P][a] * e->c[C_Q][a]) / total;
         return;
     }

@@ -1043,13 +1043,22 @@ __device__ void phase_reward(C &c)
     const int F = c.layout().F, nA = a.n_agents;
     const double *P = c.cf(C_P), *Q = c.cf(C_Q);
     if (a.flags & CATS_FLAG_REWARD_RMS) {
-        // cats.py:548-549: Python sum() over the RL firms, then over the others, left to right
+        // cats.py:548-549: Python's built-in sum() over the RL firms' revenues, then over the others'.
+        // CPython >= 3.12 adds floats with Neumaier's compensated summation (Objects/bltinmodule.c);
+        // the two sums are then added plainly.  MODEL.md 5, phase 23.
         double total = 0.0;
         if (c.lane == 0) {
-            double tot_rl = 0.0, tot_other = 0.0;
-            for (int f = 0; f < nA; ++f) tot_rl = tot_rl + P[f] * Q[f];
-            for (int f = nA; f < F; ++f) tot_other = tot_other + P[f] * Q[f];
-            total = tot_rl + tot_other;
+            auto py_sum = [&](int lo, int hi) {
+                double acc = 0.0, comp = 0.0;
+                for (int f = lo; f < hi; ++f) {
+                    const double x = P[f] * Q[f], t = acc + x;
+                    if (fabs(acc) >= fabs(x)) comp = comp + ((acc - t) + x); else comp = comp + ((x - t) + acc);
+                    acc = t;
+                }
+                if (comp != 0.0 && isfinite(comp)) acc = acc + comp;
+                return acc;
+            };
+            total = py_sum(0, nA) + py_sum(nA, F);
         }
         total = __shfl_sync(FULL, total, 0);
         for (int i = c.lane; i < nA; i += 32) a.reward[c.b * nA + i] = (P[i] * Q[i]) / total;

@@ -13,9 +13,8 @@ Tolerances: linear mode is bit-exact.  Log mode (`CatsLog`) observations and act
 `math.log` / `math.exp` in the reference and through the model's own correctly-specified
 `det_log` / `det_exp` in the engine and the oracle (docs/MODEL.md 4.2): LOG_RTOL below, well inside the
 1e-9 relative band of the brief.  The market-share reward (`reward_type="rms"`) divides by
-`sum([...])` over Python floats (cats.py:548-549): CPython <= 3.11 adds left to right -- what the
-oracle and the kernel do -- while CPython >= 3.12 (the interpreter that recorded these vectors)
-uses compensated summation, so that one quantity is compared within RMS_RTOL (a few ulp).
+`sum([...])` over Python floats (cats.py:548-549); CPython >= 3.12 -- the interpreter that recorded these
+vectors -- adds them with compensated summation, and so do the oracle and the kernel: bit-exact too.
 """
 from pathlib import Path
 
@@ -26,7 +25,6 @@ from oracle import oracle as orc
 
 GOLD = Path(__file__).resolve().parent / "golden" / "reference_driver.npz"
 LOG_RTOL, LOG_ATOL = 1e-12, 1e-13
-RMS_RTOL = 1e-15
 
 # name -> (class name, ctor kwargs, seed); the action scripts are in the file
 SCENARIOS = {
@@ -63,9 +61,7 @@ def same_bits(a, b):
 
 
 def check(a, b, log_mode, what, rms=False):
-    if rms and not log_mode:
-        np.testing.assert_allclose(a, b, rtol=RMS_RTOL, atol=0.0, err_msg=what)
-    elif log_mode:
+    if log_mode:
         np.testing.assert_allclose(a, b, rtol=LOG_RTOL, atol=LOG_ATOL, equal_nan=True, err_msg=what)
     else:
         assert same_bits(a, b), f"{what}: {np.asarray(a).ravel()[:6]} vs {np.asarray(b).ravel()[:6]}"

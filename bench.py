@@ -315,7 +315,7 @@ def run_b200(args):
                                  "markets, not by bandwidth; see DESIGN.md 2.3"},
             "clocks": clocks, "launch": env.launch_info(), "mean_unemployment_check": un_mean,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # reported at N = 1 only (the host cores are busy driving N ranks otherwise)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:

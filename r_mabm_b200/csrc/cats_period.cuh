@@ -883,15 +883,21 @@ __device__ void phase_goods_market(C &c)
             // ---- walk: dirty lanes register demand seller by seller until one has stock
             // (a round nearly always has a walker -- the chunk's first round, or the lane that just
             // exhausted a seller -- so the test comes after the step)
-            do {
+            auto walk_step = [&]() {
+                int cnd;
+                if (!cl.pop(cnd)) term = TERM_NONE;   // every candidate is sold out
+                else {
+                    const double2 yr = mkt.yr[cnd];   // stock, 1 / price
+                    fx_red(&acc[cnd], xb);
+                    if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
+                }
+            };
+            do {   // up to three steps per vote (measured: 1 -> 2 -> 3 steps +0.9 %, +2.0 %; all five -1 %):
+                   // late in the market most walks are longer than one step
                 if (term == TERM_WALK) {
-                    int cnd;
-                    if (!cl.pop(cnd)) term = TERM_NONE;   // every candidate is sold out
-                    else {
-                        const double2 yr = mkt.yr[cnd];   // stock, 1 / price
-                        fx_red(&acc[cnd], xb);
-                        if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
-                    }
+                    walk_step();
+                    if (term == TERM_WALK) walk_step();
+                    if (term == TERM_WALK) walk_step();
                 }
             } while (__any_sync(FULL, term == TERM_WALK));
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order

@@ -122,7 +122,10 @@ class FusedQPolicy(BatchedQPolicy):
         self._nat, self._lib = nat, nat.load()
         self.seed, self.economy_base, self.step_count = int(seed), int(economy_base), 0
         self.last = torch.zeros((B, n_agents, 4), dtype=torch.int32, device=self.device)
-        self.actions = torch.zeros((B, n_agents, 2), dtype=torch.float64, device=self.device)
+        # two action buffers, written alternately: the actions of the step in flight stay readable (loggers,
+        # tests) while the next ones are being chosen, without a copy
+        self._act_bufs = [torch.zeros((B, n_agents, 2), dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.actions = self._act_bufs[0]
 
     def _launch(self, obs, reward, terminated, do_train: bool, do_act: bool, active=None) -> None:
         import ctypes as C
@@ -143,6 +146,8 @@ class FusedQPolicy(BatchedQPolicy):
         a.d_obs = obs.data_ptr()
         a.d_reward = reward.data_ptr() if reward is not None else None
         a.d_terminated = terminated.data_ptr() if terminated is not None else None
+        if do_act:
+            self.actions = self._act_bufs[self.step_count & 1]
         a.d_last = self.last.data_ptr(); a.d_actions = self.actions.data_ptr()
         a.d_active = active.data_ptr() if active is not None else None
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -199,7 +204,7 @@ class BatchedRollout:
         self.t = 0
         self._next_actions = None
         self.t_b.zero_(); self.episodes.zero_()
-        self.obs = self.env.observation().clone()
+        self.obs = self.env.observation()
         return self.obs
 
     def step(self, train: bool = True):
@@ -212,7 +217,7 @@ class BatchedRollout:
         obs, reward, terminated, _ = self.env.step(actions)
         if fused:
             # two launches per rollout step: the period kernel, then TD update + next action in one
-            self.last_actions = actions.clone()
+            # (`actions` stays valid: the policy writes the next ones into its other buffer)
             self._next_actions = self.policy.train_and_act(reward, obs, terminated)
         elif train:
             self.policy.train(reward, obs, terminated)
@@ -227,7 +232,8 @@ class BatchedRollout:
             self.t_b.masked_fill_(done, 0)
             self.episodes += done.to(torch.int32)
             obs = self.env.observation()
-        self.obs = obs.clone()
+        # a view of the engine's observation buffer: valid until the next step overwrites it
+        self.obs = obs
         return reward, terminated
 
     def run(self, n_steps: int, train: bool = True) -> torch.Tensor:

@@ -45,6 +45,9 @@ extern "C" {
 #define CATS_FLAG_LOG 2u         /* CatsLog transforms, cats.py:655-704 */
 #define CATS_FLAG_AVG_PRICE 4u   /* price_change == "avg_price", cats.py:450-451 */
 #define CATS_FLAG_REWARD_RMS 8u  /* reward_type == "rms", cats.py:544-556 */
+#define CATS_FLAG_STRICT 16u     /* plain arithmetic (docs/MODEL.md 4.6): purchases and real values divide by the price, demand at a
+                                    seller is an fp64 sum in visiting order.  Slower; the mode a tape recorded from ABCredit.jl
+                                    would be replayed in if the reference divides.  Not with d_active. */
 
 /* per-economy status bits (replace the reference's warnings.warn, cats.py:518,535) */
 #define CATS_STATUS_DEPVAL_DIV0 1u
@@ -118,7 +121,8 @@ typedef struct cats_step_args {
     double *d_obs;              /* out [B][n_agents][2]  (cats.py:466-481) or NULL */
     double *d_reward;           /* out [B][n_agents]     (cats.py:493-556) or NULL */
     uint8_t *d_terminated;      /* out [B]               (cats.py:483-486) or NULL */
-    uint32_t *d_status;         /* out [B], OR-ed CATS_STATUS_* or NULL */
+    uint32_t *d_status;         /* out [B] or NULL: the CATS_STATUS_* bits raised by THIS call (the reference warns on the step
+                                   where the event occurs, cats.py:516-536); scal slot "status" keeps the sticky OR since cats_init */
     double *d_stats;            /* out [B][n_periods][CATS_N_STATS] or NULL */
     const uint8_t *d_tape;      /* replay: [B][n_periods] records of cats_tape_bytes(); NULL = Philox */
     int32_t tape_z[3];          /* z_c, z_k, z_e the tape records were laid out with (only read when d_tape != NULL) */
@@ -128,7 +132,8 @@ typedef struct cats_step_args {
     void *d_debug;              /* debug: [B][cats_workset_bytes] image of the on-chip working set */
     void *stream;
     const uint8_t *d_active;    /* DEVICE [B] or NULL: economies with a zero entry sit this call out (state
-                                   and outputs untouched); NULL = all.  See cats_reset_masked(). */
+                                   and outputs untouched); NULL = all.  See cats_reset_masked().  Cannot be combined with
+                                   d_tape, stop_phase or d_debug (CATS_EINVAL). */
     int32_t z_all[3];           /* z_c, z_k, z_e when EVERY economy of the call has exactly these values; zeros =
                                    unknown or mixed.  Only a hint for picking a kernel instantiation (the reference's
                                    defaults 5, 2, 5 at the default size have one with the lists unrolled); an economy

@@ -63,6 +63,7 @@ enum { MKT_JOB = 0, MKT_CAP = 1, MKT_GOODS = 2 };
 #define FLAG_LOG         2u   /* CatsLog action/observation transform (cats.py:655-704) */
 #define FLAG_AVG_PRICE   4u   /* price_change == "avg_price" (cats.py:450-451) */
 #define FLAG_REWARD_RMS  8u   /* reward_type == "rms" (cats.py:544-556) */
+#define FLAG_STRICT     16u   /* plain arithmetic (docs/MODEL.md 4.6): b / P, sequential Yd, no reciprocals */
 
 #define STATUS_DEPVAL_DIV0  1u  /* cats.py:516-523 ZeroDivisionError branch taken */
 #define STATUS_PROFIT_NAN   2u  /* cats.py:533-535 NaN profits set to 0 */
@@ -92,6 +93,7 @@ typedef struct {
     int bankruptcy_reward_set;
     double bankruptcy_reward;
     int stop_phase; /* debug: stop the period after this phase id (0 = run all) */
+    int strict;     /* FLAG_STRICT of the step in progress (docs/MODEL.md 4.6) */
 } Econ;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -184,7 +186,7 @@ static double det_sum(const double *x, int n)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Philox-4x32-10 (Salmon et al. 2011), counter = (agent, phase<<8|block, episode<<20|period,   */
+/* Philox-4x32-10 (Salmon et al. 2011), counter = (agent, episode<<12|phase<<8|block, period,   */
 /* economy), key = (seed_lo, seed_hi)                                                          */
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                           uint32_t k1, uint32_t out[4])
@@ -205,8 +207,9 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 static void econ_philox(const Econ *e, uint32_t agent, uint32_t phase, uint32_t block,
                         uint32_t out[4])
 {
-    uint32_t period = (uint32_t)e->scal[S_timestep] + ((uint32_t)e->scal[S_episode] << 20);
-    philox4x32_10(agent, (phase << 8) | block, period, e->economy, (uint32_t)e->seed,
+    uint32_t period = (uint32_t)e->scal[S_timestep];
+    uint32_t epi = (uint32_t)e->scal[S_episode] << 12;
+    philox4x32_10(agent, (phase << 8) | block | epi, period, e->economy, (uint32_t)e->seed,
                   (uint32_t)(e->seed >> 32), out);
 }
 
@@ -743,14 +746,14 @@ void ph_capital_market(Econ *e)
             if (!(cb > 0.0 && kd > 0.0)) break;
             int best = cand[k];
             double pk = Pk[best];
-            double afford = cb * rp[best];
+            double afford = e->strict ? cb / pk : cb * rp[best];
             double want = afford < kd ? afford : kd;
             e->k[K_Yd][best] = e->k[K_Yd][best] + want;
             double ys = e->k_Ystock[best];
             if (ys > 0.0) {
                 double full = kd * pk;
                 double spend = cb < full ? cb : full;
-                double q = spend * rp[best];
+                double q = e->strict ? spend / pk : spend * rp[best];
                 if (ys > q) {
                     e->k_Ystock[best] = ys - q;
                     kd = kd - q; cb = cb - spend;
@@ -810,11 +813,11 @@ void ph_cons_budget(Econ *e)
         double inc = h < e->W ? e->income[h]
                    : h < e->W + e->F ? e->c[C_div_income][h - e->W]
                                      : e->k[K_div_income][h - e->W - e->F];
-        double ir = inc * rpavg;
+        double ir = e->strict ? inc / price : inc * rpavg;
         double pm = e->perm[h] * xi + (1.0 - xi) * ir;
         e->perm[h] = pm;
         double pa = e->PA[h];
-        double target = pm + (chi * pa) * rpavg;
+        double target = pm + (e->strict ? (chi * pa) / price : (chi * pa) * rpavg);
         double b = target * price;
         if (b > pa) b = pa;
         if (!(b > 0.0)) b = 0.0;
@@ -858,10 +861,12 @@ void ph_goods_market(Econ *e)
             if (!(b > 0.0)) break;
             int best = cand[k];
             double p = P[best];
-            acc[best] += fx_from(b * rpavg);
+            double dem = 0.0;
+            if (e->strict) { dem = b / p; e->c[C_Yd][best] = e->c[C_Yd][best] + dem; }   /* in visiting order */
+            else acc[best] += fx_from(b * rpavg);
             double ys = e->c_Ystock[best];
             if (ys > 0.0) {
-                double d = b * rp[best];
+                double d = e->strict ? dem : b * rp[best];
                 if (ys > d) {
                     e->c_Ystock[best] = ys - d;
                     b = 0.0;
@@ -875,7 +880,7 @@ void ph_goods_market(Econ *e)
         e->budget[h] = b;
     }
     for (int f = 0; f < e->F; ++f) {
-        e->c[C_Yd][f] = (fx_to(acc[f]) * pavg) * rp[f];
+        if (!e->strict) e->c[C_Yd][f] = (fx_to(acc[f]) * pavg) * rp[f];
         e->c[C_Q][f] = e->c[C_Y_prev][f] - e->c_Ystock[f]; /* sold = produced - left over */
     }
     free(acc); free(rp);
@@ -1187,6 +1192,7 @@ void oracle_step(Econ *e, const double *actions, const uint8_t *mask, int n_agen
     double *pde = prevDe, *pp = prevP;
     if (n_agents > 64) { pde = (double *)xcalloc((size_t)n_agents, 8); pp = (double *)xcalloc((size_t)n_agents, 8); }
     e->tape = tape;
+    e->strict = (flags & FLAG_STRICT) != 0;
     /* transients carry nothing across periods: clear them so that debug images are well defined */
     memset(e->c_Ld, 0, 4u * (size_t)e->F); memset(e->c_vac, 0, 4u * (size_t)e->F);
     memset(e->k_Ld, 0, 4u * (size_t)e->N); memset(e->k_vac, 0, 4u * (size_t)e->N);
@@ -1334,6 +1340,27 @@ static void fill_stats(const Econ *e, double *st)
     st[7] = s[S_inflationRate]; st[8] = s[S_consumption]; st[9] = s[S_totK];
     st[10] = s[S_dividendsB]; st[11] = s[S_profitsB]; st[12] = s[S_GB]; st[13] = s[S_deficitGDP];
     st[14] = s[S_gov_bonds]; st[15] = s[S_price_k];
+}
+
+/* The same driver with a draw tape [B][n_periods] records and step flags (FLAG_STRICT ...).
+ * fill != 0: each record is first written with what the Philox source would draw (oracle_fill_tape) and
+ * then replayed; fill == 0: the records are the caller's (a foreign generator).  tape == NULL: Philox. */
+void oracle_run_batch_tape(Econ **econs, int B, int n_periods, uint8_t *tape, int fill, unsigned flags,
+                           double *stats, int n_threads)
+{
+    (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+    for (int b = 0; b < B; ++b) {
+        const size_t tb = tape ? econ_tl(econs[b]).bytes : 0;
+        for (int t = 0; t < n_periods; ++t) {
+            uint8_t *rec = tape ? tape + ((size_t)b * (size_t)n_periods + (size_t)t) * tb : NULL;
+            if (rec && fill) oracle_fill_tape(econs[b], rec);
+            oracle_step(econs[b], NULL, NULL, 0, FLAG_BURNIN | flags, rec, NULL, NULL);
+            if (stats) fill_stats(econs[b], stats + ((size_t)b * (size_t)n_periods + (size_t)t) * N_STATS);
+        }
+    }
 }
 
 void oracle_run_batch(Econ **econs, int B, int n_periods, double *stats, int n_threads)

@@ -42,7 +42,7 @@ C_FIELDS = ["De", "P", "Y_prev", "Yd", "Q", "A", "K", "investment", "capital_val
 K_FIELDS = ["De", "P", "Y_prev", "Yd", "Q", "A", "wages", "interests", "deb", "liquidity",
             "interest_r", "div_income", "inv", "Yavail"]
 
-FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS = 1, 2, 4, 8
+FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS, FLAG_STRICT = 1, 2, 4, 8, 16
 N_STATS = 16
 
 
@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
         L.oracle_sample_distinct.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_perm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_run_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_run_batch_tape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint,
+                                            C.c_void_p, C.c_int]
         L.oracle_obs.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p]
         _lib = L
     return _lib
@@ -193,13 +195,25 @@ class OracleEconomy:
 
 
 def run_batch(econs: list[OracleEconomy], n_periods: int, n_threads: int = 1,
-              want_stats: bool = True) -> np.ndarray | None:
-    """Advance every economy n_periods heuristic periods (OpenMP over economies)."""
+              want_stats: bool = True, tape: np.ndarray | None = None, fill_tape: bool = False,
+              flags: int = 0) -> np.ndarray | None:
+    """Advance every economy n_periods heuristic periods (OpenMP over economies).
+    tape: uint8 [B, n_periods, tape_bytes]; with fill_tape the records are first written with the
+    Philox source's draws and then replayed, otherwise they are the caller's (a foreign generator).
+    flags: extra step flags (FLAG_STRICT)."""
     L = lib()
     B = len(econs)
     arr = (C.c_void_p * B)(*[e._h for e in econs])
     stats = np.zeros((B, n_periods, N_STATS), dtype=np.float64) if want_stats else None
-    L.oracle_run_batch(arr, B, n_periods, stats.ctypes.data if want_stats else None, n_threads)
+    sp = stats.ctypes.data if want_stats else None
+    if tape is None and not flags:
+        L.oracle_run_batch(arr, B, n_periods, sp, n_threads)
+    else:
+        if tape is not None:
+            assert tape.dtype == np.uint8 and tape.flags.c_contiguous
+            assert tape.shape == (B, n_periods, econs[0].tape_bytes()), tape.shape
+        L.oracle_run_batch_tape(arr, B, n_periods, tape.ctypes.data if tape is not None else None,
+                                int(fill_tape), flags, sp, n_threads)
     return stats
 
 

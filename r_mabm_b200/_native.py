@@ -19,7 +19,7 @@ N_SCAL = 32
 N_STATS = 16
 MAX_Z = 8
 
-FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS = 1, 2, 4, 8
+FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS, FLAG_STRICT = 1, 2, 4, 8, 16
 STATUS_DEPVAL_DIV0, STATUS_PROFIT_NAN, STATUS_Z_MISMATCH = 1, 2, 4
 OK, EINVAL, ECUDA, ESMEM = 0, -1, -2, -3
 

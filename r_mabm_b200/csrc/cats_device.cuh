@@ -142,12 +142,13 @@ struct DrawsT {
     const unsigned char *tape;  // nullptr => Philox
     const uint32_t *rk;         // Philox round keys (kernel parameter space)
     uint32_t period, economy;
+    uint32_t epi;               // episode << 12: rides in counter word 1 above the phase and block bits
     const TapeOff *tp;          // tape record layout (kernel parameter space: costs no registers)
     const int *tape_z;          // z_c, z_k, z_e the tape was laid out with
 
     __device__ __forceinline__ uint4 philox(uint32_t agent, uint32_t phase, uint32_t block) const
     {
-        return philox4x32_10(agent, (phase << 8) | block, period, economy, rk);
+        return philox4x32_10(agent, (phase << 8) | block | epi, period, economy, rk);
     }
     __device__ __forceinline__ double uniform(uint32_t phase, int agent) const
     {

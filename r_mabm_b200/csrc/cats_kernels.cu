@@ -91,6 +91,7 @@ __device__ __forceinline__ void q_row_max(const double *row, int m, int lane, do
         const int oa = __shfl_xor_sync(FULL, arg, off);
         if (ov > best || (ov == best && oa < arg)) { best = ov; arg = oa; }
     }
+    if (arg == 0x7fffffff) arg = 0;   // a row of NaNs compares false everywhere: act on cell 0, as numpy's argmax of such a row does
 }
 
 __global__ void cats_q_kernel(const __grid_constant__ QArgs q)
@@ -157,8 +158,9 @@ static bool is_default_size(const Layout &L)
 }
 // production: Philox draws, no debug stop, no debug image
 static KernelFn select_kernel(const Layout &L, int max_z, int g, bool masked = false, bool production = true,
-                              bool default_z = false)
+                              bool default_z = false, bool strict = false)
 {
+    if (strict) return kernel_strict(!production ? 0 : (default_z && is_default_size(L)) ? 2 : 1, g);
     if (masked) return kernel_masked(g);   // resets are rare: one instantiation serves every size and z
     if (!production) return kernel_debug(max_z, g);
     if (default_z && is_default_size(L)) return kernel_static(g);
@@ -405,6 +407,12 @@ int cats_step(const cats_step_args *s)
         return fail(CATS_EINVAL, "multi-period launches take no actions (use the BURNIN flag)%s", "");
     if (s->stop_phase && s->n_periods != 1) return fail(CATS_EINVAL, "stop_phase needs n_periods == 1%s", "");
     if (((uintptr_t)s->d_blobs & 127u) != 0) return fail(CATS_EINVAL, "d_blobs must be 128-byte aligned%s", "");
+    // the masked kernel is a production instantiation (Philox draws, whole periods, no debug image): a call that
+    // combines d_active with a replay tape or a debug stop would silently get Philox-drawn whole periods
+    if (s->d_active && (s->d_tape || s->stop_phase || s->d_debug))
+        return fail(CATS_EINVAL, "d_active cannot be combined with d_tape, stop_phase or d_debug%s", "");
+    if (s->d_active && (s->flags & CATS_FLAG_STRICT))
+        return fail(CATS_EINVAL, "d_active cannot be combined with CATS_FLAG_STRICT%s", "");
     if (s->B == 0) return CATS_OK;
 
     KArgs a;
@@ -439,7 +447,8 @@ int cats_step(const cats_step_args *s)
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
     const bool default_z = s->z_all[0] == DefaultLayout::kZc && s->z_all[1] == DefaultLayout::kZk && s->z_all[2] == DefaultLayout::kZe;
-    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, !s->d_tape && !s->stop_phase && !s->d_debug, default_z);
+    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, !s->d_tape && !s->stop_phase && !s->d_debug, default_z,
+                                (s->flags & CATS_FLAG_STRICT) != 0);
     if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
     fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
     g_launches++;

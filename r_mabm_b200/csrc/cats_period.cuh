@@ -82,10 +82,14 @@ template <> struct LastPhase<true> {
 // MODE 1: production -- draws come from Philox only, no debug stop, no debug image.
 // MODE 2: production for the reference's default configuration -- the layout (W=1000, F=100, N=20) and
 //         the candidate-list lengths (z_c=5, z_k=2, z_e=5) are compile-time constants (DefaultLayout) too.
-template <int MODE>
+// STRICT: the plain arithmetic of docs/MODEL.md 4.6 (CATS_FLAG_STRICT): purchases and real values divide by the
+//         price instead of multiplying by a once-rounded reciprocal, and the demand registered at a
+//         consumption-goods seller is an fp64 sum in visiting order instead of an order-free fixed-point one.
+template <int MODE, bool STRICT_ = false>
 struct CtxT {
     static constexpr bool kStatic = MODE == 2;   // layout resolved at compile time
     static constexpr bool kProd = MODE >= 1;     // Philox only, no debug stop / image
+    static constexpr bool kStrict = STRICT_;
     static constexpr bool ST = kStatic;
     __device__ __forceinline__ decltype(auto) layout() const
     {
@@ -127,7 +131,7 @@ struct CtxT {
     __device__ __forceinline__ int *iat(int off) const { return reinterpret_cast<int *>(sm + off); }
 };
 
-enum { M_STATUS = 0, M_EPISODE = 1 };   // M_EPISODE: the economy's episode counter << 20 (Philox counter word 2)
+enum { M_STATUS = 0, M_EPISODE = 1 };   // M_EPISODE: the economy's episode counter << 12 (Philox counter word 1, above phase | block)
 constexpr int JOB_SORT_MAX = 128;   // job search: up to this many seekers are sorted by position (see phase_job_search)
 
 __device__ __forceinline__ double bfly(double a)
@@ -565,7 +569,7 @@ __device__ void phase_produce(C &c)
         double Pl = 0.0;
         if (Y > 0.0) Pl = (1.01 * (((wages + interests) + ((Y / k) * eta) * pk) + theta * deb)) / Y;
         if (P < Pl) { P = Pl; c.cf(C_P)[f] = P; }
-        mkt.yr[f] = make_double2(Y, 1.0 / P); mkt.p[f] = P; mkt.cls[f] = 0u;
+        mkt.yr[f] = make_double2(Y, C::kStrict ? 0.0 : 1.0 / P); mkt.p[f] = P; mkt.cls[f] = 0u;   // strict: .y is the Yd accumulator
         c.cf(C_investment)[f] = 0.0; c.at(L.s_cvalinv)[f] = 0.0;
         c.cf(C_Yd)[f] = 0.0;                     // == the all-zero demand accumulator of the goods market
         if (last < 20) c.cf(C_Q)[f] = 0.0;       // else written when the goods market closes
@@ -664,14 +668,14 @@ __device__ void phase_capital_market(C &c)
                     if (k < z && cb > 0.0 && kd > 0.0) {
                         const int best = cand[k];
                         const double pk = pr[k], rpk = RPk[best];
-                        const double afford = cb * rpk;
+                        const double afford = C::kStrict ? cb / pk : cb * rpk;
                         const double want = afford < kd ? afford : kd;
                         Ydk[best] = Ydk[best] + want;
                         const double ys = Ysk[best];
                         if (ys > 0.0) {
                             const double full = kd * pk;
                             const double spend = cb < full ? cb : full;
-                            const double q = spend * rpk;
+                            const double q = C::kStrict ? spend / pk : spend * rpk;
                             if (ys > q) {
                                 Ysk[best] = ys - q;
                                 kd = kd - q; cb = cb - spend;
@@ -735,9 +739,9 @@ __device__ void phase_households_only(C &c)
         else inc = h < L.W + L.F ? c.cf(C_div_income)[h - L.W] : c.kf(K_div_income)[h - L.W - L.F];
         if (c.last >= 19) {
             const double rpavg = 1.0 / price;
-            double ir = inc * rpavg;
+            double ir = C::kStrict ? inc / price : inc * rpavg;
             pm = pm * xi + (1.0 - xi) * ir;
-            double target = pm + (chi * pa) * rpavg;
+            double target = pm + (C::kStrict ? (chi * pa) / price : (chi * pa) * rpavg);
             double b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
@@ -815,7 +819,8 @@ __device__ void phase_goods_market(C &c)
         const double xi = c.par()[P_xi];
         const double net = wb * (1.0 - c.par()[P_tax_rate]);
         const double rp = 1.0 / price;
-        gk[G_net] = net; gk[G_sub] = sub; gk[G_ir_emp] = net * rp; gk[G_ir_un] = sub * rp;
+        gk[G_net] = net; gk[G_sub] = sub;
+        gk[G_ir_emp] = C::kStrict ? net / price : net * rp; gk[G_ir_un] = C::kStrict ? sub / price : sub * rp;
         gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = rp;
     }
     __syncwarp();
@@ -849,9 +854,9 @@ __device__ void phase_goods_market(C &c)
             const double price = gk[G_price];
             double ir;
             if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
-            else ir = dinc * rpavg;
+            else ir = C::kStrict ? dinc / price : dinc * rpavg;
             pm = pm * gk[G_xi] + gk[G_omxi] * ir;
-            const double target = pm + (gk[G_chi] * pa) * rpavg;
+            const double target = pm + (C::kStrict ? (gk[G_chi] * pa) / price : (gk[G_chi] * pa) * rpavg);
             b = target * price;
             if (b > pa) b = pa;
             if (!(b > 0.0)) b = 0.0;
@@ -878,7 +883,11 @@ __device__ void phase_goods_market(C &c)
         enum { TERM_NONE = -1, TERM_WALK = -2 };
         int term = b > 0.0 ? TERM_WALK : TERM_NONE;
         double d_t = 0.0;
-        unsigned long long xb = fx_from(b * rpavg);   // this lane's demand in real units, fixed point
+        unsigned long long xb = C::kStrict ? 0ull : fx_from(b * rpavg);   // this lane's demand in real units, fixed point
+        // strict mode: the demand b / P of every visit, in the order of the (sorted) candidate list; added to
+        // the sellers' accumulators in visiting order when the chunk is done
+        const auto cl0 = cl;
+        int nv = 0; double vv[C::kStrict ? ZM : 1];
         while (pend) {
             // ---- walk: dirty lanes register demand seller by seller until one has stock
             // (a round nearly always has a walker -- the chunk's first round, or the lane that just
@@ -888,8 +897,16 @@ __device__ void phase_goods_market(C &c)
                 if (!cl.pop(cnd)) term = TERM_NONE;   // every candidate is sold out
                 else {
                     const double2 yr = mkt.yr[cnd];   // stock, 1 / price
-                    fx_red(&acc[cnd], xb);
-                    if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
+                    if constexpr (C::kStrict) {
+                        const double dem = b / mkt.p[cnd];
+#pragma unroll
+                        for (int k = 0; k < ZM; ++k) if (k == nv) vv[k] = dem;
+                        ++nv;
+                        if (yr.x > 0.0) { term = cnd; d_t = dem; }
+                    } else {
+                        fx_red(&acc[cnd], xb);
+                        if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
+                    }
                 }
             };
             do {   // up to three steps per vote (measured: 1 -> 2 -> 3 steps +0.9 %, +2.0 %; all five -1 %):
@@ -933,7 +950,7 @@ __device__ void phase_goods_market(C &c)
                         b = b - ys * mkt.p[seller]; ys = 0.0;
                         term = b > 0.0 ? TERM_WALK : TERM_NONE;
                         done = term == TERM_NONE;
-                        xb = fx_from(b * rpavg);
+                        if constexpr (!C::kStrict) xb = fx_from(b * rpavg);
                     }
                     if (lastp) mkt.yr[seller].x = ys;
                 }
@@ -944,6 +961,20 @@ __device__ void phase_goods_market(C &c)
             __syncwarp();
         }
         if (h >= 0) c.PA(h) = pa + b;   // involuntary saving
+        if constexpr (C::kStrict) {
+            // Yd += b / P at every seller visited, household by household in visiting order (= lane order)
+            unsigned m = __ballot_sync(FULL, nv > 0);
+            while (m) {
+                const int l = __ffs(m) - 1; m &= m - 1;
+                if (lane == l) {
+                    auto c2 = cl0;
+#pragma unroll
+                    for (int k = 0; k < ZM; ++k)
+                        if (k < nv) { int sl = 0; c2.pop(sl); mkt.yr[sl].y = mkt.yr[sl].y + vv[k]; }
+                }
+                __syncwarp();
+            }
+        }
     }
     // close: unpack the seller records.  The reductions above were issued by other lanes: fence, then
     // read the accumulators where they live (L2)
@@ -954,7 +985,7 @@ __device__ void phase_goods_market(C &c)
         for (int f = lane; f < F; f += 32) {
             const double2 r = mkt.yr[f];
             const unsigned long long a = __ldcg(&acc[f]);
-            Yd[f] = (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
+            Yd[f] = C::kStrict ? r.y : (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
         }
     }
     __syncwarp();
@@ -1359,12 +1390,12 @@ __device__ void run_period(C &c)
 // (measured: the same source with the test compiled in is 3 % slower even when active == nullptr).
 // MODE: see CtxT.  The host picks 2 when (W, F, N) == (1000, 100, 20) and the slice is not padded, 0 when
 // the call carries a tape, a debug stop or a debug image, 1 otherwise.
-template <int ZM, int G, int MINB, bool MASKED, int MODE>
+template <int ZM, int G, int MINB, bool MASKED, int MODE, bool STRICT = false>
 __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_block[];
     constexpr bool ST = MODE == 2, PROD = MODE >= 1;
-    CtxT<MODE> c;
+    CtxT<MODE, STRICT> c;
     c.a = &a;
     const auto &L = c.layout();
     const int slice = ST ? ((DefaultLayout::smem + 15) & ~15) : a.slice;
@@ -1408,7 +1439,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
         for (int i = L.resident / 4 + c.lane; i < L.s_par / 4; i += 32) reinterpret_cast<int *>(smem)[i] = 0;
     __syncwarp();
     mbar_wait(bar, 0);
-    if (c.lane == 0) c.misc()[M_EPISODE] = (int)((uint32_t)c.scal()[S_episode] << 20);
+    if (c.lane == 0) c.misc()[M_EPISODE] = (int)((uint32_t)c.scal()[S_episode] << 12);
     __syncwarp();
 
     c.d.rk = a.rk;
@@ -1416,10 +1447,13 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     c.d.tp = &a.T;
     c.d.tape_z = a.tape_z;
 
+    unsigned launch_status = 0u;   // lane 0: the status bits raised by THIS launch (what d_status reports)
     for (int t = 0; t < a.n_periods; ++t) {
         if (G > 1 && t > 0) __syncthreads();   // back in step (see above)
-        // counter word 2: period in the low 20 bits, episode (bumped by a masked reset) above them
-        c.d.period = (uint32_t)c.scal()[S_timestep] + (uint32_t)c.misc()[M_EPISODE];
+        // counter word 2: the period (32 bits); the episode (bumped by a masked reset) has its own 20 bits
+        // in word 1, so neither a long episode nor many resets can alias another stream (MODEL.md 3.1)
+        c.d.period = (uint32_t)c.scal()[S_timestep];
+        c.d.epi = (uint32_t)c.misc()[M_EPISODE];
         if constexpr (!PROD)
             c.d.tape = a.tape ? a.tape + ((size_t)b * (size_t)a.n_periods + (size_t)t) * (size_t)a.T.bytes : nullptr;
         run_period<ZM, G>(c);
@@ -1439,8 +1473,10 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
             }
             a.stats[((size_t)b * (size_t)a.n_periods + (size_t)t) * N_STATS + c.lane] = v;
         }
-        if (c.lane == 0 && c.misc()[M_STATUS])
-            c.scal()[S_status] = (double)((unsigned)c.scal()[S_status] | (unsigned)c.misc()[M_STATUS]);
+        if (c.lane == 0 && c.misc()[M_STATUS]) {
+            launch_status |= (unsigned)c.misc()[M_STATUS];
+            c.scal()[S_status] = (double)((unsigned)c.scal()[S_status] | (unsigned)c.misc()[M_STATUS]);   // sticky copy
+        }
         __syncwarp();
     }
     // a26 _get_obs (cats.py:466-481 / 655-671), a21 terminated, status
@@ -1458,7 +1494,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     }
     if (c.lane == 0) {
         if (a.terminated) a.terminated[b] = c.scal()[S_terminated] != 0.0 ? 1 : 0;
-        if (a.status) a.status[b] = (unsigned)c.scal()[S_status] | (bad_z ? CATS_STATUS_Z_MISMATCH : 0u);
+        if (a.status) a.status[b] = launch_status | (bad_z ? CATS_STATUS_Z_MISMATCH : 0u);
     }
     if (!PROD && a.debug) {
         // transients image (cats_workset_field_info): Ld vac cFtot cKdem cYstock cvalinv kFtot kYstock
@@ -1505,16 +1541,16 @@ constexpr int kThreads = 32;    // one warp per economy
 constexpr int kMaxPerSM = 28;
 typedef void (*KernelFn)(const KArgs);
 
-template <int ZM, bool MASKED, int MODE>
+template <int ZM, bool MASKED, int MODE, bool STRICT = false>
 static KernelFn select_group(int g)
 {
     switch (g) {
-    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2, MASKED, MODE>;
-    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4, MASKED, MODE>;
-    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8, MASKED, MODE>;
-    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12, MASKED, MODE>;
-    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14, MASKED, MODE>;
-    default: return cats_period_kernel<ZM, 1, kMaxPerSM, MASKED, MODE>;
+    case 2: return cats_period_kernel<ZM, 2, kMaxPerSM / 2, MASKED, MODE, STRICT>;
+    case 4: return cats_period_kernel<ZM, 4, kMaxPerSM / 4, MASKED, MODE, STRICT>;
+    case 8: return cats_period_kernel<ZM, 8, kMaxPerSM / 8, MASKED, MODE, STRICT>;
+    case 12: return cats_period_kernel<ZM, 12, kMaxPerSM / 12, MASKED, MODE, STRICT>;
+    case 14: return cats_period_kernel<ZM, 14, kMaxPerSM / 14, MASKED, MODE, STRICT>;
+    default: return cats_period_kernel<ZM, 1, kMaxPerSM, MASKED, MODE, STRICT>;
     }
 }
 
@@ -1524,6 +1560,7 @@ KernelFn kernel_debug(int max_z, int g);    // MODE 0: tape / debug stop / debug
 KernelFn kernel_prod(int max_z, int g);     // MODE 1: any size
 KernelFn kernel_static(int g);              // MODE 2: default size, z <= 5
 KernelFn kernel_masked(int g);              // MODE 1 + per-economy active mask (resets), any z
+KernelFn kernel_strict(int mode, int g);    // CATS_FLAG_STRICT: MODE 0 / 1 (any z), MODE 2 (default configuration)
 
 }  // namespace cats
 #endif

@@ -32,7 +32,10 @@ class BatchedCats:
                  params: Dict[str, Any] | list | None = None, n_agents: int = 0,
                  reward_type: str = "profits", price_change: str = "agent_price",
                  log_mode: bool = False, bankruptcy_reward: float = -100.0, seed: int = 0,
-                 economy_base: int = 0, device: str | torch.device = "cuda"):
+                 economy_base: int = 0, device: str | torch.device = "cuda", strict: bool = False):
+        # strict: the plain arithmetic of docs/MODEL.md 4.6 (CATS_FLAG_STRICT) -- divisions by the price and
+        # an fp64 demand sum in visiting order instead of reciprocals and the order-free fixed-point sum
+        self.strict = bool(strict)
         if reward_type not in ("profits", "rms"):
             raise ValueError("Invalid reward type. Must be 'profits' or 'rms'")
         if price_change not in ("agent_price", "avg_price"):
@@ -120,6 +123,8 @@ class BatchedCats:
             f |= nat.FLAG_AVG_PRICE
         if self.reward_type == "rms":
             f |= nat.FLAG_REWARD_RMS
+        if self.strict:
+            f |= nat.FLAG_STRICT
         return f
 
     def _stream(self) -> int:
@@ -160,6 +165,8 @@ class BatchedCats:
 
     def _args(self, n_periods: int, flags: int, actions=None, mask=None, stats=None, tape=None,
               stop_phase: int = 0, debug=None, want_io: bool = True, active=None) -> nat.StepArgs:
+        if active is not None and (tape is not None or stop_phase or debug is not None):
+            raise ValueError("`active` cannot be combined with a replay tape, stop_phase or a debug image")
         a = nat.StepArgs()
         a.d_blobs = self._blob.data_ptr(); a.B = self.B
         a.W, a.F, a.N = self.W, self.F, self.N

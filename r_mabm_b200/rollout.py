@@ -212,6 +212,8 @@ class BatchedRollout:
         if fused and self._next_actions is not None:
             actions = self._next_actions          # chosen by the launch that trained on the last transition
         else:
+            # an action cached by an earlier fused step was chosen for an older observation: drop it
+            self._next_actions = None
             actions = self.policy.get_action(self.obs)
         self.last_actions = actions      # kept for loggers / tests; never leaves the device
         obs, reward, terminated, _ = self.env.step(actions)

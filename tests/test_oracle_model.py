@@ -201,3 +201,61 @@ def test_oracle_reset_starts_a_new_episode_with_a_fresh_stream():
     assert not np.array_equal(a.i32("Oc"), b.i32("Oc"))         # ... different draws
     a.reset()
     assert a.scal("episode") == 2.0
+
+
+def test_strict_mode_is_a_healthy_economy_and_differs_from_the_fast_rules():
+    """MODEL.md 4.6: FLAG_STRICT = plain divisions and a sequential fp64 demand sum.  Same invariants;
+    integer state parts ways with the fast rules within a few dozen periods (deviations register)."""
+    a = orc.OracleEconomy(1000, 100, 20, seed=0, economy=0)
+    b = orc.OracleEconomy(1000, 100, 20, seed=0, economy=0)
+    first = None
+    for t in range(1, 61):
+        a.step()
+        b.step(flags=orc.FLAG_BURNIN | orc.FLAG_STRICT)
+        _invariants(b, 1000, 100, 20)
+        if first is None and not np.array_equal(a.i32("Oc"), b.i32("Oc")):
+            first = t
+    assert first is not None and first <= 30, first
+    # one period from the same state: float state within the band a reciprocal can explain
+    c = orc.OracleEconomy(300, 30, 8, seed=4, economy=1)
+    d = orc.OracleEconomy(300, 30, 8, seed=4, economy=1)
+    c.step(); d.step(flags=orc.FLAG_BURNIN | orc.FLAG_STRICT)
+    assert np.array_equal(c.i32("Oc"), d.i32("Oc"))
+    assert np.allclose(c.f64("PA"), d.f64("PA"), rtol=1e-9, atol=1e-12)
+
+
+def test_batch_driver_with_tape_and_flags_equals_single_steps():
+    """oracle_run_batch_tape: Philox records filled and replayed == plain Philox stepping; a foreign tape
+    through the batch driver == through step(); strict flag carried."""
+    from tape_util import foreign_tapes
+    W, F, N, T = 200, 20, 5, 6
+    a = [orc.OracleEconomy(W, F, N, seed=9, economy=i) for i in range(3)]
+    b = [orc.OracleEconomy(W, F, N, seed=9, economy=i) for i in range(3)]
+    recs = np.zeros((3, T, a[0].tape_bytes()), dtype=np.uint8)
+    sa = orc.run_batch(a, T, n_threads=3, tape=recs, fill_tape=True)
+    sb = orc.run_batch(b, T, n_threads=1)
+    assert np.array_equal(sa.view(np.uint64), sb.view(np.uint64)) and recs.any()
+    for x, y in zip(a, b):
+        assert np.array_equal(x.i32("Oc"), y.i32("Oc")) and np.array_equal(x.f64("PA"), y.f64("PA"))
+    rng = np.random.default_rng(1)
+    ft = foreign_tapes(rng, 3 * T, W, F, N, 5, 2, 5).reshape(3, T, -1)
+    assert ft.shape[2] == a[0].tape_bytes()
+    orc.run_batch(a, T, n_threads=3, tape=ft, fill_tape=False, flags=orc.FLAG_STRICT, want_stats=False)
+    for i, y in enumerate(b):
+        for t in range(T):
+            y.step(flags=orc.FLAG_BURNIN | orc.FLAG_STRICT, tape=ft[i, t])
+        _invariants(y, W, F, N)
+        assert np.array_equal(a[i].i32("Oc"), y.i32("Oc")) and np.array_equal(a[i].f64("c_Yd"), y.f64("c_Yd"))
+
+
+def test_episode_has_its_own_counter_bits():
+    """MODEL.md 3.1: the episode rides in counter word 1 (20 bits), the period has all of word 2 -- a long
+    episode cannot run into the next episode's stream."""
+    e = orc.OracleEconomy(50, 5, 2, seed=1, economy=0)
+    base = e.fill_tape()
+    e.f64("scal")[orc.SCAL_NAMES.index("timestep")] = float(1 << 20)      # was: aliased episode 1, period 0
+    late = e.fill_tape()
+    e.f64("scal")[orc.SCAL_NAMES.index("timestep")] = 0.0
+    e.f64("scal")[orc.SCAL_NAMES.index("episode")] = 1.0
+    ep1 = e.fill_tape()
+    assert not np.array_equal(late, ep1) and not np.array_equal(base, ep1) and not np.array_equal(base, late)

@@ -5,6 +5,9 @@
 // Build note: this translation unit is compiled with -fmad=false.  The spec's arithmetic is
 // "every * and + rounds separately", which is what makes the kernels bit-exact against the CPU
 // oracle (gcc -ffp-contract=off).
+//
+// CATS_EMU: defined only by tests/simt (a CPU emulation of warps and blocks that compiles this source with
+// g++ to check the kernel's logic without a GPU).  The inline PTX below then has plain-C++ stand-ins.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -371,7 +374,11 @@ __device__ __forceinline__ void fx_add(unsigned long long *acc, unsigned long lo
 // the same add on an accumulator in global memory: one fire-and-forget 64-bit reduction at L2
 __device__ __forceinline__ void fx_red(unsigned long long *acc, unsigned long long x)
 {
+#ifdef CATS_EMU
+    *acc += x;
+#else
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(acc), "l"(x) : "memory");
+#endif
 }
 
 // a / b, bit-identical to the IEEE quotient.  The compiler's fp64 division drops into a ~60
@@ -382,7 +389,9 @@ __device__ __forceinline__ double div_nz(double a, double b)
 {
     const bool z = (a == 0.0) && (b > 0.0) && (b < __longlong_as_double(0x7ff0000000000000LL));
     double num = z ? 1.0 : a;
+#ifndef CATS_EMU
     asm volatile("" : "+d"(num));   // keep the compiler from folding this back into a / b
+#endif
     const double q = num / b;
     return z ? a : q;
 }
@@ -396,6 +405,20 @@ __device__ __forceinline__ int d2count(double x)
 
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier
+#ifdef CATS_EMU
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { simt::mbar_arrive(bar); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t) { simt::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { simt::mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) { simt::mbar_wait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gsrc, bytes); }
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *, uint32_t) {}
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_all() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -458,5 +481,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // exit and give the memory back; the writes themselves complete with the grid)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#endif  // CATS_EMU
 
 }  // namespace cats

@@ -1393,7 +1393,11 @@ __device__ void run_period(C &c)
 template <int ZM, int G, int MINB, bool MASKED, int MODE, bool STRICT = false>
 __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_constant__ KArgs a)
 {
+#ifdef CATS_EMU
+    unsigned char *smem_block = simt::g_blk->smem;
+#else
     extern __shared__ __align__(128) unsigned char smem_block[];
+#endif
     constexpr bool ST = MODE == 2, PROD = MODE >= 1;
     CtxT<MODE, STRICT> c;
     c.a = &a;

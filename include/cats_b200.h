@@ -226,6 +226,11 @@ void cats_debug_set_group(int economies_per_block);
  * kernel for them too; 1 (default) restores the specialisation.  Results never depend on it. */
 void cats_debug_set_static(int on);
 
+/* Debug aid: warps per economy for later cats_step calls: 1 = the one-warp-per-economy kernel, 2 / 4 / 8 = the
+ * multi-warp kernel (one thread block per economy, for launches that would leave the GPU under-filled), 0 = chosen per
+ * launch from the batch size (default).  Results never depend on it. */
+void cats_debug_set_warps(int warps_per_economy);
+
 #ifdef __cplusplus
 }
 #endif

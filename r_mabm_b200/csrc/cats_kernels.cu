@@ -11,6 +11,7 @@
 #include "cats_period.cuh"
 
 #include "cats_aux.cuh"
+#include "cats_period_mw.cuh"
 
 // =============================================================================================
 // C-ABI
@@ -21,6 +22,7 @@ static std::atomic<unsigned long long> g_launches{0};
 static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
 static int g_group = 0;                // debug: set by cats_debug_set_group() (0 = automatic)
 static int g_static = 1;               // debug: cats_debug_set_static(0) keeps the generic kernel for the default size
+static int g_warps = 0;                // debug: cats_debug_set_warps(): warps per economy (0 = chosen per launch)
 // development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
 static int smem_pad()
 {
@@ -78,6 +80,28 @@ static int choose_group(const Layout &L, long long B, int sms)
     return best;
 }
 
+// Warps per economy.  The one-warp kernel fills the GPU from about 28 x SMs economies up; a smaller launch takes as
+// long as ONE economy's dependent chain, so several warps share an economy instead (cats_period_mw.cuh): as many as
+// keep ~28 warps on every SM, if the block's shared memory still lets every economy of the launch be resident.
+static int choose_warps(const Layout &L, long long B, int sms)
+{
+    static int env_forced = -1;
+    if (env_forced < 0) { const char *e = getenv("CATS_WARPS"); env_forced = e ? atoi(e) : 0; }
+    const int forced = g_warps ? g_warps : env_forced;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    if (sms < 1) sms = 1;
+    const long long want = (long long)kMaxPerSM * sms / (B > 0 ? B : 1);
+    const int cand[3] = {8, 4, 2};
+    for (int i = 0; i < 3; ++i) {
+        const int nw = cand[i];
+        if (want < nw) continue;
+        const long long bytes = slice_bytes(L) + mw_extra_bytes(nw) + 1024;
+        const long long fit = (228 * 1024) / bytes;
+        if (bytes <= 227 * 1024 && fit * sms >= B) return nw;
+    }
+    return 1;
+}
+
 static int fail(int code, const char *fmt, const char *detail)
 {
     snprintf(g_err, sizeof g_err, fmt, detail);
@@ -116,6 +140,7 @@ void cats_debug_phase_cycles(void *d_cycles16) { g_cycles = (long long *)d_cycle
 void cats_debug_set_group(int economies_per_block) { g_group = economies_per_block; }
 
 void cats_debug_set_static(int on) { g_static = on ? 1 : 0; }
+void cats_debug_set_warps(int warps_per_economy) { g_warps = warps_per_economy; }
 
 size_t cats_blob_bytes(int W, int F, int N)
 {
@@ -197,6 +222,20 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
     return CATS_OK;
 }
 
+
+static int configure_smem(KernelFn fn, int smem)
+{
+    int dev = 0, max_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
+    return CATS_OK;
+}
 
 static int configure_kernel(const Layout &L, KernelFn fn, int g, int *blocks_per_sm, int *num_sms)
 {
@@ -299,14 +338,24 @@ int cats_step(const cats_step_args *s)
     int occ = 0, sms = 0;
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int g = choose_group(a.L, s->B, nsm);
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
     const bool default_z = s->z_all[0] == DefaultLayout::kZc && s->z_all[1] == DefaultLayout::kZk && s->z_all[2] == DefaultLayout::kZe;
-    KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, !s->d_tape && !s->stop_phase && !s->d_debug, default_z,
-                                (s->flags & CATS_FLAG_STRICT) != 0);
-    if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
-    fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
+    const bool production = !s->d_tape && !s->stop_phase && !s->d_debug;
+    const bool strict = (s->flags & CATS_FLAG_STRICT) != 0;
+    const int nw = (production && !strict && !s->d_active) ? choose_warps(a.L, s->B, nsm) : 1;
+    if (nw > 1) {
+        // one block = one economy, nw warps (cats_period_mw.cuh)
+        KernelFn fn = kernel_mw((default_z && is_default_size(a.L)) ? 2 : 1, s->max_z, nw);
+        const int smem = a.slice + mw_extra_bytes(nw);
+        if (int rc = configure_smem(fn, smem)) return rc;
+        fn<<<(unsigned)s->B, kThreads * nw, smem, (cudaStream_t)s->stream>>>(a);
+    } else {
+        const int g = choose_group(a.L, s->B, nsm);
+        KernelFn fn = select_kernel(a.L, s->max_z, g, s->d_active != nullptr, production, default_z, strict);
+        if (int rc = configure_kernel(a.L, fn, g, &occ, &sms)) return rc;
+        fn<<<(unsigned)((s->B + g - 1) / g), kThreads * g, a.slice * g, (cudaStream_t)s->stream>>>(a);
+    }
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cats_step launch: %s", cudaGetErrorString(e));

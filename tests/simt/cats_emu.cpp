@@ -3,6 +3,7 @@
 #include "simt_emu.h"
 
 #include "../../r_mabm_b200/csrc/cats_aux.cuh"
+#include "../../r_mabm_b200/csrc/cats_period_mw.cuh"
 
 using namespace cats;
 
@@ -15,9 +16,31 @@ void run(const KArgs &a)
     simt::launch(grid, 32u * G, (size_t)a.slice * G, [&]() { cats_period_kernel<ZM, G, 1, MASKED, MODE, STRICT>(a); });
 }
 
+template <int ZM, int NW, int MODE>
+void run_mw(const KArgs &a)
+{
+    simt::launch((unsigned)a.B, 32u * NW, (size_t)a.slice + MWLayout<NW>::bytes, [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE>(a); });
+}
+
 }  // namespace
 
 extern "C" {
+
+// the multi-warp kernel: nw warps per economy; mode 1 (any size) or 2 (default configuration)
+int emu_step_mw(const cats_step_args *s, int mode, int nw)
+{
+    KArgs a;
+    fill_kargs(s, a);
+    if (s->d_tape || s->stop_phase || s->d_debug || s->d_active || (s->flags & CATS_FLAG_STRICT)) return -1;
+    if (mode == 2) {
+        if (s->W != DefaultLayout::kW || s->F != DefaultLayout::kF || s->N != DefaultLayout::kN) return -1;
+        if (nw == 2) run_mw<5, 2, 2>(a); else if (nw == 4) run_mw<5, 4, 2>(a); else run_mw<5, 8, 2>(a);
+    } else {
+        if (nw == 2) run_mw<MAX_Z, 2, 1>(a); else if (nw == 4) run_mw<MAX_Z, 4, 1>(a); else run_mw<MAX_Z, 8, 1>(a);
+    }
+    return 0;
+}
+
 
 void emu_set_schedule(int s) { simt::g_schedule = s; }
 

@@ -46,7 +46,10 @@ static void on_exit_fiber()
         w.arrived = 0; w.present = 0; w.gen++;
     }
     b.live--;
-    if (b.bar_arrived > 0 && b.bar_arrived == b.live) { b.bar_arrived = 0; b.bar_gen++; }
+    if (b.bar_arrived > 0 && b.bar_arrived == b.live) {
+        b.bar_res[b.bar_gen & 1] = b.bar_acc; b.bar_rescnt[b.bar_gen & 1] = b.bar_cnt;
+        b.bar_acc = 0; b.bar_cnt = 0; b.bar_arrived = 0; b.bar_gen++;
+    }
     simt_switch(&f.sp, b.sched_sp);
     die("resumed a finished fiber");
 }

@@ -53,6 +53,8 @@ struct Block {
     int live = 0;
     int bar_arrived = 0;
     unsigned bar_gen = 0;
+    int bar_acc = 0, bar_cnt = 0;     // __syncthreads_or / _count: the reduction of the barrier in progress
+    int bar_res[2] = {0, 0}, bar_rescnt[2] = {0, 0};
     // named barriers (bar.sync id, count): arrival counts and generations
     int nb_arrived[16] = {0};
     unsigned nb_gen[16] = {0};
@@ -178,13 +180,20 @@ template <class T> inline unsigned __match_any_sync(unsigned mask, T v)
         }
     });
 }
-inline void __syncthreads()
+inline int simt_block_barrier(int pred, bool count)
 {
     simt::Block &b = *simt::g_blk;
     const unsigned gen = b.bar_gen;
-    if (++b.bar_arrived == b.live) { b.bar_arrived = 0; b.bar_gen = gen + 1; b.progress++; }
-    else while (b.bar_gen == gen) simt::yield();
+    b.bar_acc |= pred ? 1 : 0; b.bar_cnt += pred ? 1 : 0;
+    if (++b.bar_arrived == b.live) {
+        b.bar_res[gen & 1] = b.bar_acc; b.bar_rescnt[gen & 1] = b.bar_cnt;
+        b.bar_acc = 0; b.bar_cnt = 0; b.bar_arrived = 0; b.bar_gen = gen + 1; b.progress++;
+    } else while (b.bar_gen == gen) simt::yield();
+    return count ? b.bar_rescnt[gen & 1] : b.bar_res[gen & 1];
 }
+inline void __syncthreads() { simt_block_barrier(0, false); }
+inline int __syncthreads_or(int pred) { return simt_block_barrier(pred, false); }
+inline int __syncthreads_count(int pred) { return simt_block_barrier(pred, true); }
 // bar.sync id, count
 inline void simt_named_barrier(int id, int count)
 {

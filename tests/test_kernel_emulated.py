@@ -120,3 +120,35 @@ def test_masked_reset_and_episode_stream():
     env.run(5)
     orc.run_batch(orcs, 5, want_stats=False)
     assert compare_state(env, orcs, "after masked reset + 5") == []
+
+
+@pytest.mark.parametrize("W,F,N,warps,mode,schedule", [(1000, 100, 20, 4, 2, 0), (1000, 100, 20, 8, 1, 3), (1000, 100, 20, 2, 2, 1),
+                                                         (300, 30, 8, 4, 1, 1), (130, 7, 2, 8, 1, 6), (37, 3, 1, 2, 1, 0),
+                                                         (2000, 200, 40, 8, 1, 1)])
+def test_multiwarp_kernel_matches_oracle(W, F, N, warps, mode, schedule):
+    """cats_period_mw.cuh: one block per economy, `warps` warps, the wide goods market with commit rule R2."""
+    B, T = 2, 60
+    env = EmuCats(B, W=W, F=F, N=N, seed=23, mode=mode, warps=warps, schedule=schedule)
+    orcs = make_oracles(B, W, F, N, seed=23)
+    for t0 in range(0, T, 20):
+        stats = env.run(20, want_stats=True)
+        ref = orc.run_batch(orcs, 20, n_threads=B)
+        bad = compare_state(env, orcs, f"{warps} warps t={t0 + 20}")
+        assert bad == [], "\n".join(bad)
+        assert np.array_equal(stats.view(np.uint64), ref.view(np.uint64))
+
+
+def test_multiwarp_rl_step():
+    B, A, W, F, N = 2, 2, 300, 30, 8
+    env = EmuCats(B, W=W, F=F, N=N, n_agents=A, seed=17, mode=1, warps=4, schedule=1)
+    orcs = make_oracles(B, W, F, N, seed=17)
+    env.run(20)
+    orc.run_batch(orcs, 20, want_stats=False)
+    rng = np.random.default_rng(5)
+    for t in range(5):
+        acts = rng.uniform(0.7, 1.3, size=(B, A, 2))
+        obs, rew, term, _ = env.step(acts)
+        for b, o in enumerate(orcs):
+            r_obs, r_rew = o.step(actions=acts[b], flags=0)
+            assert np.array_equal(bits(obs[b]), bits(r_obs)) and np.array_equal(bits(rew[b]), bits(r_rew))
+        assert compare_state(env, orcs, f"t={t}") == []

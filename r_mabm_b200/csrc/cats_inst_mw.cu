@@ -15,5 +15,5 @@ KernelFn kernel_mw(int mode, int max_z, int nw)
     if (mode == 2) return mw_pick<5, 2>(nw);
     return (max_z > 0 && max_z <= 5) ? mw_pick<5, 1>(nw) : mw_pick<MAX_Z, 1>(nw);
 }
-int mw_extra_bytes(int nw) { return nw == 2 ? MWLayout<2>::bytes : nw == 4 ? MWLayout<4>::bytes : MWLayout<8>::bytes; }
+int mw_extra_bytes(int nw, int F) { return nw == 2 ? MWLayout<2>::total(F) : nw == 4 ? MWLayout<4>::total(F) : MWLayout<8>::total(F); }
 }  // namespace cats

@@ -95,7 +95,7 @@ static int choose_warps(const Layout &L, long long B, int sms)
     for (int i = 0; i < 3; ++i) {
         const int nw = cand[i];
         if (want < nw) continue;
-        const long long bytes = slice_bytes(L) + mw_extra_bytes(nw) + 1024;
+        const long long bytes = slice_bytes(L) + mw_extra_bytes(nw, L.F) + 1024;
         const long long fit = (228 * 1024) / bytes;
         if (bytes <= 227 * 1024 && fit * sms >= B) return nw;
     }
@@ -347,7 +347,7 @@ int cats_step(const cats_step_args *s)
     if (nw > 1) {
         // one block = one economy, nw warps (cats_period_mw.cuh)
         KernelFn fn = kernel_mw((default_z && is_default_size(a.L)) ? 2 : 1, s->max_z, nw);
-        const int smem = a.slice + mw_extra_bytes(nw);
+        const int smem = a.slice + mw_extra_bytes(nw, a.L.F);
         if (int rc = configure_smem(fn, smem)) return rc;
         fn<<<(unsigned)s->B, kThreads * nw, smem, (cudaStream_t)s->stream>>>(a);
     } else {

@@ -186,15 +186,16 @@ __device__ __forceinline__ void credit_one(const C &c, double need, double b1, d
 
 // a3-a8: every per-firm decision of the period in one pass (phases 3..10).  No cross-firm
 // dependence: the bank rations against its start-of-period equity.
+// The per-firm loops over C-firms [f_lo, f_hi) and K-firms [k_lo, k_hi): the whole population for the one-warp
+// kernel, one warp's 32-aligned share in the multi-warp kernel (which takes the sums from shared memory instead).
 template <class C>
-__device__ void phase_firm_decisions(C &c)
+__device__ __forceinline__ void firm_decisions_loops(C &c, int f_lo, int f_hi, int k_lo, int k_hi, double &accC, double &accK)
 {
     const auto &L = c.layout();
-    const int F = L.F, N = L.N, last = c.last;
+    const int F = L.F, last = c.last;
     const double alpha = c.par()[P_alpha], q_adj = c.par()[P_q_adj], p_adj = c.par()[P_p_adj];
     const double wb = c.scal()[S_wb];
-    double accC = 0.0, accK = 0.0;  // det_sum partials of new credit
-    for (int f = c.lane; f < F; f += 32) {
+    for (int f = f_lo + c.lane; f < f_hi; f += 32) {
         double *De = c.cf(C_De), *P = c.cf(C_P);
         // every row value this firm needs, loaded before the first store (the rows share one base
         // pointer: the compiler will not move a load over a store on its own)
@@ -267,7 +268,7 @@ __device__ void phase_firm_decisions(C &c)
         }
         De[f] = de; P[f] = p;
     }
-    for (int i = c.lane; i < N; i += 32) {
+    for (int i = k_lo + c.lane; i < k_hi; i += 32) {
         double *De = c.kf(K_De), *P = c.kf(K_P);
         const double Yprev = c.kf(K_Y_prev)[i], Yd = c.kf(K_Yd)[i], avail = c.kf(K_Yavail)[i];
         double p = P[i], de = De[i];
@@ -302,6 +303,17 @@ __device__ void phase_firm_decisions(C &c)
             c.vac()[F + i] = vac;
         }
     }
+}
+
+// a3-a8: every per-firm decision of the period in one pass (phases 3..10).  No cross-firm
+// dependence: the bank rations against its start-of-period equity.
+template <class C>
+__device__ void phase_firm_decisions(C &c)
+{
+    const auto &L = c.layout();
+    const int last = c.last;
+    double accC = 0.0, accK = 0.0;  // det_sum partials of new credit
+    firm_decisions_loops(c, 0, L.F, 0, L.N, accC, accK);
     // bank loan stock: += det_sum(new credit), C-firms then K-firms
     if (last >= 9) {
         accC = bfly(accC); accK = bfly(accK);
@@ -318,6 +330,62 @@ __device__ void phase_firm_decisions(C &c)
 // employees with the smallest (fire_key, worker index).  The employees of the over-staffed firms
 // are bucketed by firm (count, prefix, scatter) and every pooled worker ranks itself inside its
 // firm's bucket; rank < s means dismissed.  The result does not depend on the bucket order.
+// One batch of phase_fire: consecutive firms [f0, f1) whose pooled employees fit a pool of `cap` entries;
+// writes each firm's bucket start into ic[f] (count | start << 16) and returns the entries pooled.  One warp.
+template <class C>
+__device__ __forceinline__ int fire_batch(C &c, int *ic, int f0, int limit, int cap, int &f1_out)
+{
+    const int lane = c.lane;
+    int base = 0, f1 = f0;
+    bool stop = false;
+    while (!stop && f1 < limit) {
+        const int f = f1 + lane;
+        const int n = f < limit ? ic[f] : 0;
+        int incl = n;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
+        const unsigned fm = __ballot_sync(FULL, base + incl <= cap);
+        const int nfit = fm == FULL ? 32 : __ffs(~fm) - 1;
+        if (f < limit && lane < nfit) ic[f] = n | ((base + incl - n) << 16);
+        const int add = __shfl_sync(FULL, incl, nfit > 0 ? nfit - 1 : 0);
+        if (nfit > 0) base += add;
+        f1 += nfit;
+        if (nfit < 32) stop = true;
+    }
+    if (f1 > limit) f1 = limit;
+    f1_out = f1;
+    return base;
+}
+
+// the slow path of phase_fire for ONE firm whose employees do not fit the pool: s arg-min selections over all
+// workers.  One warp.
+template <class C>
+__device__ __forceinline__ void fire_oversize(C &c, int f)
+{
+    const int W = c.layout().W, lane = c.lane;
+    const int s = -c.vac()[f];
+    for (int r = 0; r < s; ++r) {
+        unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
+        for (int w = lane; w < W; w += 32) {
+            if (c.Oc()[w] == f) {
+                unsigned key = c.d.fire_key(w);
+                if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            unsigned ok = __shfl_xor_sync(FULL, bk, off);
+            int ow = __shfl_xor_sync(FULL, bw, off);
+            if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
+        }
+        if (bw == 0x7fffffff) break;
+        if (lane == 0) c.Oc()[bw] = -1;
+        __syncwarp();
+    }
+    if (lane == 0) { c.Leff()[f] = c.Leff()[f] + c.vac()[f]; c.vac()[f] = 0; }
+    __syncwarp();
+}
+
 template <class C>
 __device__ void phase_fire(C &c, int limit)
 {
@@ -335,52 +403,15 @@ __device__ void phase_fire(C &c, int limit)
     int f0 = 0;
     while (f0 < limit) {
         // batch [f0, f1): consecutive firms whose pooled employees fit the pool
-        int base = 0, f1 = f0;
-        bool stop = false;
-        while (!stop && f1 < limit) {
-            const int f = f1 + lane;
-            const int n = f < limit ? ic[f] : 0;
-            int incl = n;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
-            const unsigned fm = __ballot_sync(FULL, base + incl <= cap);
-            const int nfit = fm == FULL ? 32 : __ffs(~fm) - 1;
-            if (f < limit && lane < nfit) ic[f] = n | ((base + incl - n) << 16);
-            const int add = __shfl_sync(FULL, incl, nfit > 0 ? nfit - 1 : 0);
-            if (nfit > 0) base += add;
-            f1 += nfit;
-            if (nfit < 32) stop = true;
-        }
-        if (f1 > limit) f1 = limit;
+        int f1;
+        const int total = fire_batch(c, ic, f0, limit, cap, f1);
         __syncwarp();
         if (f1 == f0) {
             // one firm larger than the pool: s arg-min selections over all workers (slow, rare)
-            const int f = f0;
-            const int s = -c.vac()[f];
-            for (int r = 0; r < s; ++r) {
-                unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
-                for (int w = lane; w < W; w += 32) {
-                    if (c.Oc()[w] == f) {
-                        unsigned key = c.d.fire_key(w);
-                        if (key < bk || (key == bk && w < bw)) { bk = key; bw = w; }
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    unsigned ok = __shfl_xor_sync(FULL, bk, off);
-                    int ow = __shfl_xor_sync(FULL, bw, off);
-                    if (ok < bk || (ok == bk && ow < bw)) { bk = ok; bw = ow; }
-                }
-                if (bw == 0x7fffffff) break;
-                if (lane == 0) c.Oc()[bw] = -1;
-                __syncwarp();
-            }
-            if (lane == 0) { c.Leff()[f] = c.Leff()[f] + c.vac()[f]; c.vac()[f] = 0; }
-            __syncwarp();
-            f0 = f + 1;
+            fire_oversize(c, f0);
+            f0 = f0 + 1;
             continue;
         }
-        const int total = base;
         if (total > 0) {
             int fnext = lane < W ? c.Oc()[lane] : -1;
 #pragma unroll 1
@@ -419,6 +450,9 @@ __device__ void phase_fire(C &c, int limit)
 // the longest prefix of lanes whose picks cannot have been pre-empted by a lower lane is committed
 // at once (lane j is safe iff fewer than vac[f] lower lanes chose the same f), the rest retry
 // against the updated vacancies.  Outcome == the sequential visiting-order rule.
+template <int ZM, class C>
+__device__ __forceinline__ void job_match(C &c, const unsigned short *seekers, int total, bool listed);
+
 template <int ZM, class C>
 __device__ void phase_job_search(C &c)
 {
@@ -484,6 +518,24 @@ __device__ void phase_job_search(C &c)
         }
     }
     __syncwarp();
+    job_match<ZM>(c, seekers, total, listed);
+    if (!listed) {   // the bits the goods market reads instead of gathering employment links
+        for (int base = 0; base < W; base += 32) {
+            const int w = base + lane;
+            const unsigned bal = __ballot_sync(FULL, w < W && c.Oc()[w] >= 0);
+            if (lane == 0) c.emp()[base >> 5] = bal;
+        }
+    }
+    __syncwarp();
+}
+
+// The matching rounds of the job search over `total` seekers listed in visiting order.  One warp.
+template <int ZM, class C>
+__device__ __forceinline__ void job_match(C &c, const unsigned short *seekers, int total, bool listed)
+{
+    const auto &L = c.layout();
+    const int nf = L.F + L.N, lane = c.lane;
+    const int z = c.z_e() < nf ? c.z_e() : nf;
     const unsigned lt = c.lt();
     for (int base = 0; base < total; base += 32) {
         const int idx = base + lane;
@@ -515,14 +567,6 @@ __device__ void phase_job_search(C &c)
             __syncwarp();
         }
     }
-    if (!listed) {   // the bits the goods market reads instead of gathering employment links
-        for (int base = 0; base < W; base += 32) {
-            const int w = base + lane;
-            const unsigned bal = __ballot_sync(FULL, w < W && c.Oc()[w] >= 0);
-            if (lane == 0) c.emp()[base >> 5] = bal;
-        }
-    }
-    __syncwarp();
 }
 
 // One consumption-goods seller as the market sees it.  The SoA rows (P, Q, stock) are packed into
@@ -547,14 +591,14 @@ struct Mkt {
 
 // a11 firms_produce! (cats.py:384-385)
 template <class C>
-__device__ void phase_produce(C &c)
+__device__ __forceinline__ void produce_c_loop(C &c, int f_lo, int f_hi)
 {
     const auto &L = c.layout();
-    const int F = L.F, N = L.N, last = c.last;
+    const int F = L.F, last = c.last;
     const double alpha = c.par()[P_alpha], k = c.par()[P_k], eta = c.par()[P_eta], theta = c.par()[P_theta];
     const double wb = c.scal()[S_wb], pk = c.scal()[S_price_k];
     Mkt mkt(c.sm + L.s_U, F);
-    for (int f = c.lane; f < F; f += 32) {
+    for (int f = f_lo + c.lane; f < f_hi; f += 32) {
         // loads first (see phase_firm_decisions)
         const double K_f = c.cf(C_K)[f], De = c.cf(C_De)[f], deb = c.cf(C_deb)[f], ir_f = c.cf(C_interest_r)[f];
         double P = c.cf(C_P)[f];
@@ -574,6 +618,44 @@ __device__ void phase_produce(C &c)
         c.cf(C_Yd)[f] = 0.0;                     // == the all-zero demand accumulator of the goods market
         if (last < 20) c.cf(C_Q)[f] = 0.0;       // else written when the goods market closes
     }
+}
+
+template <class C>
+__device__ __forceinline__ void produce_k_loop(C &c, int k_lo, int k_hi)
+{
+    const auto &L = c.layout();
+    const int F = L.F;
+    const double alpha = c.par()[P_alpha], theta = c.par()[P_theta];
+    const double wb = c.scal()[S_wb];
+    for (int i = k_lo + c.lane; i < k_hi; i += 32) {
+        double Leff = (double)c.Leff()[F + i];
+        double want = c.kf(K_De)[i];
+        double cap_l = Leff * alpha;
+        double Y = want < cap_l ? want : cap_l;
+        c.kf(K_Y_prev)[i] = Y;
+        double avail = Y + c.kf(K_inv)[i];
+        c.at(L.s_kYstock)[i] = avail; c.kf(K_Yavail)[i] = avail;
+        double deb = c.kf(K_deb)[i];
+        double interests = c.kf(K_interest_r)[i] * deb;
+        double wages = wb * Leff;
+        c.kf(K_interests)[i] = interests; c.kf(K_wages)[i] = wages;
+        double Pl = 0.0;
+        if (Y > 0.0) Pl = (1.01 * ((wages + interests) + theta * deb)) / Y;
+        double P = c.kf(K_P)[i];
+        if (P < Pl) { P = Pl; c.kf(K_P)[i] = P; }
+        // the Q slot carries 1 / P through the capital-goods market (MODEL.md 4.5); K-firm
+        // sales are Yavail - stock, written by the accounting phase
+        c.kf(K_Q)[i] = 1.0 / P; c.kf(K_Yd)[i] = 0.0;
+    }
+}
+
+template <class C>
+__device__ void phase_produce(C &c)
+{
+    const auto &L = c.layout();
+    const int F = L.F, N = L.N, last = c.last;
+    Mkt mkt(c.sm + L.s_U, F);
+    produce_c_loop(c, 0, F);
     if (last >= 20) {
         // price classes of the sellers (prices are final for the period from here on)
         __syncwarp();
@@ -593,28 +675,7 @@ __device__ void phase_produce(C &c)
             if (f3 < F) mkt.cls[f3] = nd;
         }
     }
-    if (last >= 15) {
-        for (int i = c.lane; i < N; i += 32) {
-            double Leff = (double)c.Leff()[F + i];
-            double want = c.kf(K_De)[i];
-            double cap_l = Leff * alpha;
-            double Y = want < cap_l ? want : cap_l;
-            c.kf(K_Y_prev)[i] = Y;
-            double avail = Y + c.kf(K_inv)[i];
-            c.at(L.s_kYstock)[i] = avail; c.kf(K_Yavail)[i] = avail;
-            double deb = c.kf(K_deb)[i];
-            double interests = c.kf(K_interest_r)[i] * deb;
-            double wages = wb * Leff;
-            c.kf(K_interests)[i] = interests; c.kf(K_wages)[i] = wages;
-            double Pl = 0.0;
-            if (Y > 0.0) Pl = (1.01 * ((wages + interests) + theta * deb)) / Y;
-            double P = c.kf(K_P)[i];
-            if (P < Pl) { P = Pl; c.kf(K_P)[i] = P; }
-            // the Q slot carries 1 / P through the capital-goods market (MODEL.md 4.5); K-firm
-            // sales are Yavail - stock, written by the accounting phase
-            c.kf(K_Q)[i] = 1.0 / P; c.kf(K_Yd)[i] = 0.0;
-        }
-    }
+    if (last >= 15) produce_k_loop(c, 0, N);
     __syncwarp();
 }
 
@@ -992,16 +1053,21 @@ __device__ void phase_goods_market(C &c)
 }
 
 // a17 firms_accounting! (cats.py:397-398)
-template <class C>
-__device__ void phase_accounting(C &c)
+// The per-firm loops of the accounting phase over C-firms [f_lo, f_hi) and K-firms [k_lo, k_hi).  acc[0..5]: the
+// det_sum partials (installments, interests, dividend tax; C then K) of a warp that walks a whole population.
+// STAGE (multi-warp kernel): the summands are also left in transient rows that are dead by now (C: instalment in
+// the Kdem row, dividend tax in the valinv row; K: instalment in the Ftot row, dividend tax in the Ystock row; the
+// interests are a persisted row), for ONE warp to add up in the oracle's order afterwards.
+template <bool STAGE, class C>
+__device__ __forceinline__ void accounting_loops(C &c, int f_lo, int f_hi, int k_lo, int k_hi, double (&acc)[6])
 {
     const auto &L = c.layout();
-    const int W = L.W, F = L.F, N = L.N, last = c.last;
+    const int W = L.W, F = L.F, last = c.last;
     const double delta = c.par()[P_delta], eta = c.par()[P_eta], k = c.par()[P_k], theta = c.par()[P_theta];
     const double divs = c.par()[P_div], taxd = c.par()[P_tax_rate_d];
     const Mkt mkt(c.sm + L.s_U, F);
     double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;   // det_sum partials
-    for (int f = c.lane; f < F; f += 32) {
+    for (int f = f_lo + c.lane; f < f_hi; f += 32) {
         // loads first (see phase_firm_decisions)
         const double Yp = c.cf(C_Y_prev)[f], barYK = c.cf(C_barYK)[f], Kold = c.cf(C_K)[f];
         const double inv_f = c.cf(C_investment)[f], cv = c.cf(C_capital_value)[f], Q_f = c.cf(C_Q)[f];
@@ -1016,6 +1082,7 @@ __device__ void phase_accounting(C &c)
         double RIC = mkt.p[f] * Q_f;
         double in = theta * deb;
         double liq = ((((liq0 + RIC) + c.at(L.s_cFtot)[f]) - wages) - interests) - in;
+        if (STAGE) c.at(L.s_cKdem)[f] = in;
         c.cf(C_deb)[f] = deb - in;
         double pi = ((RIC - wages) - interests) - dv;
         double A = A0 + pi;
@@ -1029,10 +1096,11 @@ __device__ void phase_accounting(C &c)
         }
         c.cf(C_div_income)[f] = net;
         c.cf(C_liquidity)[f] = liq; c.cf(C_A)[f] = A;
+        if (STAGE) c.at(L.s_cvalinv)[f] = dt;
         s_in = s_in + in; s_int = s_int + interests; s_dt = s_dt + dt;
     }
     if (last >= 22) {
-        for (int i = c.lane; i < N; i += 32) {
+        for (int i = k_lo + c.lane; i < k_hi; i += 32) {
             const double left = c.at(L.s_kYstock)[i];
             const double Qi = c.kf(K_Yavail)[i] - left;   // sold = available - left over
             c.kf(K_Q)[i] = Qi;
@@ -1055,9 +1123,35 @@ __device__ void phase_accounting(C &c)
             }
             c.kf(K_div_income)[i] = net;
             c.kf(K_liquidity)[i] = liq; c.kf(K_A)[i] = A;
+            if (STAGE) { c.at(L.s_kFtot)[i] = in; c.at(L.s_kYstock)[i] = dt; }
             k_in = k_in + in; k_int = k_int + interests; k_dt = k_dt + dt;
         }
     }
+    acc[0] = s_in; acc[1] = s_int; acc[2] = s_dt; acc[3] = k_in; acc[4] = k_int; acc[5] = k_dt;
+}
+
+// the bank's and the government's books take the six sums
+template <class C>
+__device__ __forceinline__ void accounting_book(C &c, double s_in, double s_int, double s_dt, double k_in, double k_int, double k_dt)
+{
+    const int last = c.last;
+    {
+        double loans = c.scal()[S_bank_loans] - s_in;
+        double ii = c.scal()[S_bank_interest_income] + s_int;
+        double ta = c.scal()[S_gov_TA] + s_dt;
+        if (last >= 22) { loans = loans - k_in; ii = ii + k_int; ta = ta + k_dt; }
+        c.scal()[S_bank_loans] = loans; c.scal()[S_bank_interest_income] = ii; c.scal()[S_gov_TA] = ta;
+    }
+}
+
+template <class C>
+__device__ void phase_accounting(C &c)
+{
+    const auto &L = c.layout();
+    double acc[6];
+    accounting_loops<false>(c, 0, L.F, 0, L.N, acc);
+    double s_in = acc[0], s_int = acc[1], s_dt = acc[2], k_in = acc[3], k_int = acc[4], k_dt = acc[5];
+    const int last = c.last;
     // six det_sums: installments, interests, dividend tax for C then K
     s_in = bfly(s_in); s_int = bfly(s_int); s_dt = bfly(s_dt);
     k_in = bfly(k_in); k_int = bfly(k_int); k_dt = bfly(k_dt);
@@ -1159,8 +1253,10 @@ __device__ void phase_tracking(C &c)
 }
 
 // a20 firms_go_bankrupt! (cats.py:404) + a21 _get_terminated (cats.py:483-486)
+// flags, the masked sums over survivors / defaulters, the bank's books and the entrants.  One warp.  Returns the
+// number of bankrupt firms; their workers are released by bankrupt_release.
 template <class C>
-__device__ void phase_bankrupt(C &c)
+__device__ __forceinline__ int bankrupt_replace(C &c)
 {
     const auto &L = c.layout();
     const int W = L.W, F = L.F, N = L.N;
@@ -1250,15 +1346,31 @@ __device__ void phase_bankrupt(C &c)
             c.kf(K_div_income)[i] = 0.0;
             c.Leff()[F + i] = 0;
         }
-        for (int w0 = c.lane; w0 < W; w0 += 32 * 4) {
-            int oo[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const int w = w0 + 32 * u; oo[u] = w < W ? c.Oc()[w] : -1; }   // 4 loads in flight
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (oo[u] >= 0 && bad[oo[u]]) c.Oc()[w0 + 32 * u] = -1;
-        }
     }
-    __syncwarp();
+    return nbad;
+}
+
+// the employees of the bankrupt firms lose their jobs: workers start, start + stride, ...
+template <class C>
+__device__ __forceinline__ void bankrupt_release(C &c, int start, int stride)
+{
+    const auto &L = c.layout();
+    const int W = L.W;
+    const unsigned char *bad = c.sm + L.s_bad;
+    for (int w0 = start; w0 < W; w0 += stride * 4) {
+        int oo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int w = w0 + stride * u; oo[u] = w < W ? c.Oc()[w] : -1; }   // 4 loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (oo[u] >= 0 && bad[oo[u]]) c.Oc()[w0 + stride * u] = -1;
+    }
+}
+
+// a21 _get_terminated (cats.py:483-486).  One warp.
+template <class C>
+__device__ __forceinline__ void bankrupt_terminated(C &c)
+{
+    const int F = c.layout().F;
     {
         const double *A = c.cf(C_A);
         double s = 0.0;
@@ -1266,17 +1378,27 @@ __device__ void phase_bankrupt(C &c)
         s = bfly(s);
         if (c.lane == 0) c.scal()[S_terminated] = s == 0.0 ? 1.0 : 0.0;
     }
+}
+
+template <class C>
+__device__ void phase_bankrupt(C &c)
+{
+    const int nbad = bankrupt_replace(c);
+    if (nbad > 0) bankrupt_release(c, c.lane, 32);
+    __syncwarp();
+    bankrupt_terminated(c);
     __syncwarp();
 }
 
 // a22 bank_accounting!, a23 gov_accounting!, a24 adjust_wages!, a25 timestep (cats.py:407-413)
+// the scalar part, by ONE thread; returns each owner household's share of the bank's dividend
 template <class C>
-__device__ void phase_closing(C &c)
+__device__ __forceinline__ double closing_scalars(C &c)
 {
     const auto &L = c.layout();
     const int last = c.last;
     double share = 0.0;
-    if (c.lane == 0) {
+    {
         double *s = c.scal();
         double gross = (s[S_bank_interest_income] + s[S_gov_r_b] * s[S_gov_bonds]) - s[S_bank_bad_debt];
         double dB = 0.0;
@@ -1298,6 +1420,15 @@ __device__ void phase_closing(C &c)
         }
         if (last >= 29) s[S_timestep] = s[S_timestep] + 1.0;
     }
+    return share;
+}
+
+template <class C>
+__device__ void phase_closing(C &c)
+{
+    const auto &L = c.layout();
+    double share = 0.0;
+    if (c.lane == 0) share = closing_scalars(c);
     share = __shfl_sync(FULL, share, 0);
     if (share > 0.0)
         for (int h = L.W + c.lane; h < L.H; h += 32) c.PA(h) = c.PA(h) + share;

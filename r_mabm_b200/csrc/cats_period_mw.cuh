@@ -44,7 +44,8 @@ struct MWLayout {
     static constexpr int o_dang = o_mask + 2 * MW_ROWS * NW * 4;     // [2][MW_ROWS] i32: lowest uncertain lane that may still come here
     static constexpr int o_d = o_dang + 2 * MW_ROWS * 4;             // [T] f64: what the lane wants at its terminal
     static constexpr int o_term = o_d + T * 8;                       // [T] i32: the lane's terminal (-1: none)
-    static constexpr int bytes = (o_term + T * 4 + 15) & ~15;
+    static constexpr int bytes = (o_term + T * 4 + 15) & ~15;       // then [F] u64: the demand accumulators of the goods market
+    static constexpr int total(int F) { return bytes + ((8 * F + 15) & ~15); }
 };
 
 template <int MODE, int NW>
@@ -66,13 +67,16 @@ __device__ void mw_goods_market(C &c)
     const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
     Mkt mkt(c.sm + L.s_U, F);
-    unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
+    // demand accumulators in SHARED memory here (the one-warp kernel reduces into the Yd row in L2, fire and forget:
+    // but a block barrier waits for outstanding reductions to be acknowledged by L2, and this market has several
+    // barriers per round)
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.mw + ML::bytes);
     OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord;
     enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
     unsigned *maskb = reinterpret_cast<unsigned *>(c.mw + ML::o_mask);
     int *dangb = reinterpret_cast<int *>(c.mw + ML::o_dang);
-    volatile double *sh_d = reinterpret_cast<volatile double *>(c.mw + ML::o_d);
+    double *sh_d = reinterpret_cast<double *>(c.mw + ML::o_d);   // (block barriers order the accesses)
     volatile int *sh_term = reinterpret_cast<volatile int *>(c.mw + ML::o_term);
     if (warp == 0) {
         ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
@@ -87,9 +91,19 @@ __device__ void mw_goods_market(C &c)
     } else ord.k = c.okeys();
     for (int i = tid; i < 2 * MW_ROWS * NW; i += T) maskb[i] = 0u;
     for (int i = tid; i < 2 * MW_ROWS; i += T) dangb[i] = 0x7fffffff;
+    for (int f = tid; f < F; f += T) acc[f] = 0ull;
     __syncthreads();
     const int nch = (H + T - 1) / T;
     int parity = 0;
+    const bool exact_rows = F <= MW_ROWS;   // every seller has a table row of its own
+#ifdef CATS_PROFILE_PHASES
+    long long tq = 0;
+    const bool prof = c.a->cycles && tid == 0 && c.b == 0;
+    if (prof) tq = clock64();
+#define MWTICK(slot) do { if (prof) { long long t1 = clock64(); c.a->cycles[slot] += t1 - tq; tq = t1; } } while (0)
+#else
+#define MWTICK(slot) do { } while (0)
+#endif
 
     int h_n = -1, oc_n = -1; double pa_n = 0.0, pm_n = 0.0, dinc_n = 0.0;
     auto fetch = [&](int ch) {
@@ -145,18 +159,41 @@ __device__ void mw_goods_market(C &c)
         double d_t = 0.0;
         unsigned long long xb = fx_from(b * rpavg);
         int any = __syncthreads_or(pend);
+        MWTICK(12);
         while (any) {
+#ifdef CATS_EMU_COUNT
+            if (tid == 0) simt::g_count[0]++;
+#endif
             unsigned *mask = maskb + parity * (MW_ROWS * NW);
             int *dang = dangb + parity * MW_ROWS;
             // ---- walk: to the first seller of the list that has stock, registering demand on the way
             if (pend && term >= 0 && !(mkt.yr[term].x > 0.0)) term = TERM_WALK;   // emptied by a lane that committed
-            while (term == TERM_WALK) {
-                int cnd;
-                if (!cl.pop(cnd)) term = TERM_NONE;
+            if (term == TERM_WALK) {
+                // demand is registered at each seller passed and at the terminal.  The head of the list first (it
+                // usually has stock); if not, the stock of every seller left, read at once (independent loads)
+                int s0;
+                if (!cl.pop(s0)) term = TERM_NONE;
                 else {
-                    const double2 yr = mkt.yr[cnd];
-                    fx_red(&acc[cnd], xb);
-                    if (yr.x > 0.0) { term = cnd; d_t = b * yr.y; }
+                    const double2 yr0 = mkt.yr[s0];
+                    fx_add(&acc[s0], xb);
+                    if (yr0.x > 0.0) { term = s0; d_t = b * yr0.y; }
+                    else {
+                        auto rest = cl;
+                        int sl[ZM - 1]; double st[ZM - 1];
+#pragma unroll
+                        for (int k = 0; k < ZM - 1; ++k) { sl[k] = -1; st[k] = 0.0; if (rest.pop(sl[k])) st[k] = mkt.yr[sl[k]].x; else sl[k] = -1; }
+                        term = TERM_NONE;
+#pragma unroll
+                        for (int k = 0; k < ZM - 1; ++k) {
+                            if (term == TERM_NONE && sl[k] >= 0) {
+                                int dummy;
+                                cl.pop(dummy);
+                                fx_add(&acc[sl[k]], xb);
+                                if (st[k] > 0.0) term = sl[k];
+                            }
+                        }
+                        if (term >= 0) d_t = b * mkt.yr[term].y;
+                    }
                 }
             }
             if (pend && term == TERM_NONE) pend = false;   // nothing left to visit: what is left of b is saved
@@ -165,21 +202,36 @@ __device__ void mw_goods_market(C &c)
             if (has) { atomicOr(&mask[row * NW + warp], 1u << lane); sh_d[tid] = d_t; }
             sh_term[tid] = has ? term : -1;
             __syncthreads();
+            MWTICK(13);
             // ---- replay the lower lanes at my terminal, in lane order
             int status = ST_IDLE;
             double ys = 0.0;
             if (has) {
                 ys = mkt.yr[term].x;
                 bool sold = false;
-                for (int w2 = 0; w2 <= warp && !sold; ++w2) {
-                    unsigned m = mask[row * NW + w2];
-                    if (w2 == warp) m &= lt;
-                    while (m) {
-                        const int p = w2 * 32 + __ffs(m) - 1;
-                        m &= m - 1;
-                        if (sh_term[p] == term) {
-                            const double dp = sh_d[p];
-                            if (ys > dp) ys = ys - dp; else { sold = true; break; }
+                unsigned mw_[NW];
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) mw_[w2] = w2 < warp ? mask[row * NW + w2] : (w2 == warp ? mask[row * NW + w2] & lt : 0u);
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    unsigned m = mw_[w2];
+                    if (exact_rows) {
+                        while (m && !sold) {   // two peers' demands in flight per step
+                            const int p0 = w2 * 32 + __ffs(m) - 1; m &= m - 1;
+                            const double d0 = sh_d[p0];
+                            double d1 = 0.0; const bool two = m != 0u;
+                            if (two) { const int p1 = w2 * 32 + __ffs(m) - 1; m &= m - 1; d1 = sh_d[p1]; }
+                            if (ys > d0) ys = ys - d0; else sold = true;
+                            if (two && !sold) { if (ys > d1) ys = ys - d1; else sold = true; }
+                        }
+                    } else {
+                        while (m && !sold) {
+                            const int p = w2 * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+                            if (sh_term[p] == term) {
+                                const double dp = sh_d[p];
+                                if (ys > dp) ys = ys - dp; else sold = true;
+                            }
                         }
                     }
                 }
@@ -198,9 +250,13 @@ __device__ void mw_goods_market(C &c)
                 while (true) {
                     const bool newly = status == ST_FULL && !unc && dang[row] < tid;
                     if (newly) { unc = true; publish(); }
+#ifdef CATS_EMU_COUNT
+                    if (tid == 0) simt::g_count[1]++;
+#endif
                     if (!__syncthreads_or(newly)) break;
                 }
             }
+            MWTICK(14);
             // ---- commit
             if (status == ST_FULL && !unc) {
                 atomicMin(reinterpret_cast<unsigned long long *>(&mkt.yr[term].x), (unsigned long long)__double_as_longlong(ys - d_t));
@@ -220,25 +276,377 @@ __device__ void mw_goods_market(C &c)
                 while (rest.pop(s)) dang[s & (MW_ROWS - 1)] = 0x7fffffff;
             }
             parity ^= 1;
+            MWTICK(15);
         }
         if (h >= 0) c.PA(h) = pa + b;   // involuntary saving
     }
-    __threadfence();
     __syncthreads();
     {
         double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
         for (int f = tid; f < F; f += T) {
             const double2 r = mkt.yr[f];
-            const unsigned long long a = __ldcg(&acc[f]);
+            const unsigned long long a = acc[f];
             Yd[f] = (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
         }
     }
     __syncthreads();
+#undef MWTICK
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The phases around the goods market, split over the warps of the block.
+
+
+// warp w's 32-aligned share [lo, hi) of a population of n (reversed: the last warp takes the first share, so that a
+// small second population -- the K-firms -- lands on a warp that has no C-firms)
+template <class C>
+__device__ __forceinline__ void mw_range(const C &c, int n, bool reversed, int &lo, int &hi)
+{
+    constexpr int NW = C::kWarps;
+    const int per = ((((n + 31) >> 5) + NW - 1) / NW) << 5;
+    const int w = reversed ? NW - 1 - c.warp : c.warp;
+    lo = w * per; if (lo > n) lo = n;
+    hi = lo + per; if (hi > n) hi = n;
+}
+// block scratch outside the markets: the visiting-order key block (10 ints) and the goods-market constants (9 doubles)
+template <class C> __device__ __forceinline__ volatile int *mw_iscratch(const C &c) { return reinterpret_cast<volatile int *>(c.okeys()); }
+template <class C> __device__ __forceinline__ volatile double *mw_dscratch(const C &c) { return c.gk(); }
+
+// a3-a8 (phases 3..10): every warp its share of the firms; the new credit is summed by warp 0 from the Ftot rows
+template <class C>
+__device__ void mw_firm_decisions(C &c)
+{
+    const auto &L = c.layout();
+    int f_lo, f_hi, k_lo, k_hi;
+    mw_range(c, L.F, false, f_lo, f_hi);
+    mw_range(c, L.N, true, k_lo, k_hi);
+    double accC = 0.0, accK = 0.0;
+    firm_decisions_loops(c, f_lo, f_hi, k_lo, k_hi, accC, accK);
+    __syncthreads();
+    if (c.warp == 0) {
+        const double *Fc = c.at(L.s_cFtot), *Fk = c.at(L.s_kFtot);
+        double sC = 0.0, sK = 0.0;
+        for (int f = c.lane; f < L.F; f += 32) sC = sC + Fc[f];
+        for (int i = c.lane; i < L.N; i += 32) sK = sK + Fk[i];
+        sC = bfly(sC); sK = bfly(sK);
+        if (c.lane == 0) {
+            double loans = c.scal()[S_bank_loans] + sC;
+            loans = loans + sK;
+            c.scal()[S_bank_loans] = loans;
+        }
+    }
+}
+
+// a9 (phases 11, 12): as phase_fire; the passes over the workers and over the pool are the block's, warp 0 cuts the
+// batches.  Ends with every thread past the last barrier.
+template <class C>
+__device__ void mw_fire(C &c)
+{
+    constexpr int T = C::NT;
+    const auto &L = c.layout();
+    const int W = L.W, limit = L.F + L.N, tid = c.tid;
+    int *ic = c.iat(L.s_ic);
+    bool over = false;
+    for (int f = tid; f < limit; f += T) { const bool o = c.vac()[f] < 0; over |= o; ic[f] = o ? c.Leff()[f] : 0; }
+    if (!__syncthreads_or(over)) return;
+    const int cap = L.U_bytes / 8;
+    int *pool_w = c.iat(L.s_U);
+    unsigned *pool_k = reinterpret_cast<unsigned *>(c.sm + L.s_U) + cap;
+    volatile int *scr = mw_iscratch(c);
+    int f0 = 0;
+    while (f0 < limit) {
+        if (c.warp == 0) {
+            int f1;
+            const int total = fire_batch(c, ic, f0, limit, cap, f1);
+            if (c.lane == 0) { scr[0] = f1; scr[1] = total; }
+            __syncwarp();
+            if (f1 == f0) fire_oversize(c, f0);   // one firm larger than the pool (slow, rare)
+        }
+        __syncthreads();
+        const int f1 = scr[0], total = scr[1];
+        if (f1 == f0) { f0 = f0 + 1; __syncthreads(); continue; }
+        if (total > 0) {
+            for (int w = tid; w < W; w += T) {
+                const int f = c.Oc()[w];
+                if (f >= f0 && f < f1 && c.vac()[f] < 0) {
+                    const int slot = atomicAdd(&ic[f], 0x10000) >> 16;
+                    pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < total; i += T) {
+                const int w = pool_w[i]; const unsigned key = pool_k[i];
+                const int f = c.Oc()[w];
+                const int v = ic[f];
+                const int end = v >> 16, beg = end - (v & 0xffff);
+                int rank = 0;
+                for (int j = beg; j < end; ++j) {
+                    const unsigned kj = pool_k[j]; const int wj = pool_w[j];
+                    rank += (kj < key || (kj == key && wj < w)) ? 1 : 0;
+                }
+                if (rank < -c.vac()[f]) c.Oc()[w] = -1;
+            }
+            __syncthreads();
+        }
+        for (int f = f0 + tid; f < f1; f += T)
+            if (c.vac()[f] < 0) { c.Leff()[f] = c.Leff()[f] + c.vac()[f]; c.vac()[f] = 0; }
+        __syncthreads();
+        f0 = f1;
+    }
+}
+
+// a10 (phase 13): the block lists the unemployed (any order), asks the visiting order for their positions and ranks
+// them; warp 0 runs the matching rounds.  More seekers than the block ranks (start-up periods): the one-warp path.
+template <int ZM, class C>
+__device__ void mw_job_search(C &c)
+{
+    constexpr int NW = C::kWarps, T = C::NT;
+    const auto &L = c.layout();
+    const int W = L.W, tid = c.tid, lane = c.lane;
+    OrderT<C::kStatic ? DefaultLayout::kW : 0, !C::kProd> ord;
+    if (c.warp == 0) ord.init(c.d, MKT_JOB, c.a->od[MKT_JOB], c.okeys(), lane); else ord.k = c.okeys();
+    unsigned short *seekers = reinterpret_cast<unsigned short *>(c.sm + L.s_U);
+    const int cap3 = L.U_bytes / 6;
+    unsigned short *byidx = seekers + cap3, *posv = seekers + 2 * cap3;
+    int *cnt = reinterpret_cast<int *>(const_cast<double *>(mw_dscratch(c)));
+    if (tid == 0) cnt[0] = 0;
+    __syncthreads();
+    const int nwords = (W + 31) >> 5;
+    for (int word = c.warp; word < nwords; word += NW) {
+        const int w = word * 32 + lane;
+        const bool un = w < W && c.Oc()[w] < 0;
+        const unsigned bal = __ballot_sync(FULL, un);
+        int base = 0;
+        if (lane == 0) {
+            c.emp()[word] = ~bal;   // employed bits for the goods market (hires are added by the matching rounds)
+            if (bal) base = atomicAdd(&cnt[0], __popc(bal));
+        }
+        base = __shfl_sync(FULL, base, 0);
+        const int at = base + __popc(bal & c.lt());
+        if (un && at < cap3) byidx[at] = (unsigned short)w;
+    }
+    __syncthreads();
+    const int U = cnt[0];
+    // the seekers' visiting positions go into a bitmap of W bits; a seeker's rank in visiting order is the number of
+    // bits below its own (a prefix over the words + a population count): O(U + W / 32) instead of U * U compares.
+    // The bitmap and the word prefix live in the goods market's tables, idle until then.
+    unsigned *bitmap = reinterpret_cast<unsigned *>(c.mw);
+    int *prefix = reinterpret_cast<int *>(c.mw) + nwords;
+    if (U > cap3 || 8 * nwords > MWLayout<NW>::o_d) {   // start-up periods (everybody looks for a job) / huge W
+        if (c.warp == 0) phase_job_search<ZM>(c);
+        return;
+    }
+    for (int i = tid; i < nwords; i += T) bitmap[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < U; i += T) {
+        const int pos = ord.position_of((int)byidx[i]);
+        posv[i] = (unsigned short)pos;
+        atomicOr(&bitmap[pos >> 5], 1u << (pos & 31));
+    }
+    __syncthreads();
+    if (c.warp == 0) {
+        int run = 0;
+        for (int base = 0; base < nwords; base += 32) {
+            const int i = base + lane;
+            const int n = i < nwords ? __popc(bitmap[i]) : 0;
+            int incl = n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
+            if (i < nwords) prefix[i] = run + incl - n;
+            run += __shfl_sync(FULL, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < U; i += T) {
+        const int pos = (int)posv[i];
+        const int r = prefix[pos >> 5] + __popc(bitmap[pos >> 5] & ((1u << (pos & 31)) - 1u));
+        seekers[r] = byidx[i];
+    }
+    __syncthreads();
+    if (c.warp == 0) job_match<ZM>(c, seekers, U, true);
+}
+
+// a11 (phases 14, 15): every warp its share of the firms, then the sellers' price classes by the block
+template <class C>
+__device__ void mw_produce(C &c)
+{
+    constexpr int T = C::NT;
+    const auto &L = c.layout();
+    const int F = L.F;
+    int lo, hi;
+    mw_range(c, F, false, lo, hi);
+    produce_c_loop(c, lo, hi);
+    mw_range(c, L.N, true, lo, hi);
+    produce_k_loop(c, lo, hi);
+    __syncthreads();
+    Mkt mkt(c.sm + L.s_U, F);
+    for (int f = c.tid; f < F; f += T) {
+        const double pf = mkt.p[f];
+        unsigned n = 0u;
+#pragma unroll 4
+        for (int g = 0; g < F; ++g) n += mkt.p[g] < pf ? 1u : 0u;
+        mkt.cls[f] = n;
+    }
+}
+
+
+// a12 (phase 16): the block lists the investing firms in visiting order and prepares them (suppliers drawn and
+// price-sorted) into records; ONE thread then trades them one after the other in a tight loop -- the chain is
+// sequential by nature (buyer i sees the stock buyers < i left), and a single thread on prepared records walks it
+// without a warp hand-over per buyer; the block scatters the results back.  Records live in the goods market's
+// tables (idle until then), in batches if need be.
+template <int ZM>
+struct CapRec {
+    int f, n;
+    double kd, cb, lq, iv, vi;
+    int cand[ZM];
+    double pr[ZM];
+};
+
+template <int ZM, class C>
+__device__ void mw_capital_market(C &c)
+{
+    constexpr int NW = C::kWarps, T = C::NT;
+    const auto &L = c.layout();
+    const int F = L.F, N = L.N, lane = c.lane, tid = c.tid;
+    const int z = c.z_k() < N ? c.z_k() : N;
+    OrderT<C::kStatic ? DefaultLayout::kF : 0, !C::kProd> ord;
+    if (c.warp == 0) ord.init(c.d, MKT_CAP, c.a->od[MKT_CAP], c.okeys(), lane); else ord.k = c.okeys();
+    double *Pk = c.kf(K_P), *Ydk = c.kf(K_Yd), *Ysk = c.at(L.s_kYstock);
+    const double *RPk = c.kf(K_Q);   // 1 / P, parked there by produce
+    double *Kdem = c.at(L.s_cKdem), *Ftot = c.at(L.s_cFtot), *liq = c.cf(C_liquidity);
+    double *inv = c.cf(C_investment), *valinv = c.at(L.s_cvalinv), *wages = c.cf(C_wages);
+    int *buyers = c.iat(L.s_ic);
+    const int nchunks = (F + 31) >> 5;
+    unsigned *bal = reinterpret_cast<unsigned *>(c.mw);
+    int *pre = reinterpret_cast<int *>(c.mw) + nchunks;
+    const int rec_off = (8 * nchunks + 4 + 15) & ~15;
+    volatile int *tot = pre + nchunks;
+    CapRec<ZM> *rec = reinterpret_cast<CapRec<ZM> *>(c.mw + rec_off);
+    const int cap = (MWLayout<NW>::bytes - rec_off) / (int)sizeof(CapRec<ZM>);
+    if (cap < 1) {   // a population so large that not even the ballots fit: the one-warp code
+        __syncthreads();
+        if (c.warp == 0) phase_capital_market<ZM>(c);
+        return;
+    }
+    __syncthreads();
+    for (int chunk = c.warp; chunk < nchunks; chunk += NW) {
+        const int pos = chunk * 32 + lane;
+        bool act = false;
+        if (pos < F) act = Kdem[ord.at(pos)] > 0.0;
+        const unsigned b = __ballot_sync(FULL, act);
+        if (lane == 0) bal[chunk] = b;
+    }
+    __syncthreads();
+    if (c.warp == 0) {
+        int run = 0;
+        for (int base = 0; base < nchunks; base += 32) {
+            const int i = base + lane;
+            const int n = i < nchunks ? __popc(bal[i]) : 0;
+            int incl = n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
+            if (i < nchunks) pre[i] = run + incl - n;
+            run += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) tot[0] = run;
+    }
+    __syncthreads();
+    for (int chunk = c.warp; chunk < nchunks; chunk += NW) {
+        const unsigned b = bal[chunk];
+        if ((b >> lane) & 1u) buyers[pre[chunk] + __popc(b & c.lt())] = ord.at(chunk * 32 + lane);
+    }
+    const int total = tot[0];
+    __syncthreads();
+    for (int b0 = 0; b0 < total; b0 += cap) {
+        const int nb = total - b0 < cap ? total - b0 : cap;
+        for (int i = tid; i < nb; i += T) {
+            const int f = buyers[b0 + i];
+            const double lq = liq[f];
+            int cand[ZM]; double pr[ZM];
+#pragma unroll
+            for (int k = 0; k < ZM; ++k) { cand[k] = 0; pr[k] = __longlong_as_double(0x7ff0000000000000LL); }
+            c.d.template candidates<ZM>(PH_CAP, f, N, z, cand);
+#pragma unroll
+            for (int k = 0; k < ZM; ++k) if (k < z) pr[k] = Pk[cand[k]];
+            sort_by_price<ZM>(cand, pr, z);
+            CapRec<ZM> &r = rec[i];
+            r.f = f; r.n = z; r.kd = Kdem[f]; r.cb = (Ftot[f] + lq) - wages[f]; r.lq = lq; r.iv = 0.0; r.vi = 0.0;
+#pragma unroll
+            for (int k = 0; k < ZM; ++k) { r.cand[k] = cand[k]; r.pr[k] = pr[k]; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < nb; ++i) {
+                CapRec<ZM> &r = rec[i];
+                double kd = r.kd, cb = r.cb, lq = r.lq, iv = 0.0, vi = 0.0;
+                for (int k = 0; k < z && cb > 0.0 && kd > 0.0; ++k) {
+                    const int best = r.cand[k];
+                    const double pk = r.pr[k], rpk = RPk[best];
+                    const double afford = cb * rpk;
+                    const double want = afford < kd ? afford : kd;
+                    Ydk[best] = Ydk[best] + want;
+                    const double ys = Ysk[best];
+                    if (ys > 0.0) {
+                        const double full = kd * pk;
+                        const double spend = cb < full ? cb : full;
+                        const double q = spend * rpk;
+                        if (ys > q) {
+                            Ysk[best] = ys - q;
+                            kd = kd - q; cb = cb - spend;
+                            lq = lq - spend; iv = iv + q; vi = vi + spend;
+                        } else {
+                            const double cost = ys * pk;
+                            kd = kd - ys; cb = cb - cost;
+                            lq = lq - cost;
+                            iv = iv + ys; vi = vi + cost;
+                            Ysk[best] = 0.0;
+                        }
+                    }
+                }
+                r.kd = kd; r.lq = lq; r.iv = iv; r.vi = vi;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nb; i += T) {
+            const CapRec<ZM> &r = rec[i];
+            const int f = r.f;
+            liq[f] = r.lq; inv[f] = r.iv; valinv[f] = r.vi; Kdem[f] = r.kd;
+        }
+        __syncthreads();
+    }
+}
+
+// a17 (phases 21, 22): every warp its share; warp 0 adds the six sums up from the rows the loops staged
+template <class C>
+__device__ void mw_accounting(C &c)
+{
+    const auto &L = c.layout();
+    const int F = L.F, N = L.N;
+    int f_lo, f_hi, k_lo, k_hi;
+    mw_range(c, F, false, f_lo, f_hi);
+    mw_range(c, N, true, k_lo, k_hi);
+    double acc[6];
+    accounting_loops<true>(c, f_lo, f_hi, k_lo, k_hi, acc);
+    __syncthreads();
+    if (c.warp == 0) {
+        const double *c_in = c.at(L.s_cKdem), *c_int = c.cf(C_interests), *c_dt = c.at(L.s_cvalinv);
+        const double *k_inr = c.at(L.s_kFtot), *k_intr = c.kf(K_interests), *k_dtr = c.at(L.s_kYstock);
+        double s_in = 0.0, s_int = 0.0, s_dt = 0.0, k_in = 0.0, k_int = 0.0, k_dt = 0.0;
+        for (int f = c.lane; f < F; f += 32) { s_in = s_in + c_in[f]; s_int = s_int + c_int[f]; s_dt = s_dt + c_dt[f]; }
+        for (int i = c.lane; i < N; i += 32) { k_in = k_in + k_inr[i]; k_int = k_int + k_intr[i]; k_dt = k_dt + k_dtr[i]; }
+        s_in = bfly(s_in); s_int = bfly(s_int); s_dt = bfly(s_dt);
+        k_in = bfly(k_in); k_int = bfly(k_int); k_dt = bfly(k_dt);
+        if (c.lane == 0) accounting_book(c, s_in, s_int, s_dt, k_in, k_int, k_dt);
+        __syncwarp();
+    }
 }
 
 // One economy per block, NW warps.  MODE as in cats_period_kernel (1 = production, any size; 2 = the
-// default configuration with the layout resolved at compile time).  Version 1: warp 0 runs the phases
-// around the goods market with the one-warp code; the goods market is the block's.
+// default configuration with the layout resolved at compile time).  The matching chains of the labour and
+// capital-goods markets, the reward and the aggregate tracking are warp 0's (the one-warp code); everything else
+// is the block's.
 template <int ZM, int NW, int MINB, int MODE>
 __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __grid_constant__ KArgs a)
 {
@@ -285,38 +693,74 @@ __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __g
     c.d.tp = &a.T;
     c.d.tape_z = a.tape_z;
     unsigned launch_status = 0u;
+#ifdef CATS_PROFILE_PHASES
+    long long tk = 0;
+    const bool kprof = a.cycles && c.tid == 0 && b == 0;
+    if (kprof) tk = clock64();
+#define KTICK(slot) do { if (kprof) { long long t1 = clock64(); a.cycles[slot] += t1 - tk; tk = t1; } } while (0)
+#else
+#define KTICK(slot) do { } while (0)
+#endif
     for (int t = 0; t < a.n_periods; ++t) {
         c.d.period = (uint32_t)c.scal()[S_timestep];
         c.d.epi = (uint32_t)c.misc()[M_EPISODE];
         __syncthreads();      // everybody has read the period before thread 0 moves it on
+        if (c.tid == 0) {
+            c.scal()[S_gov_TA] = 0.0; c.scal()[S_gov_G] = 0.0;
+            c.scal()[S_bank_interest_income] = 0.0; c.scal()[S_bank_bad_debt] = 0.0;
+            c.scal()[S_gov_r_b] = c.par()[P_interest_rate];
+            c.misc()[M_STATUS] = 0;
+        }
+        KTICK(11);
+        mw_firm_decisions(c);
+        __syncthreads();
+        KTICK(0);
+        mw_fire(c);
+        __syncthreads();
+        KTICK(1);
+        mw_job_search<ZM>(c);
+        __syncthreads();
+        KTICK(2);
+        mw_produce(c);
+        __syncthreads();
+        KTICK(3);
+        mw_capital_market<ZM>(c);
+        KTICK(4);
         if (c.warp == 0) {
-            if (c.lane == 0) {
-                c.scal()[S_gov_TA] = 0.0; c.scal()[S_gov_G] = 0.0;
-                c.scal()[S_bank_interest_income] = 0.0; c.scal()[S_bank_bad_debt] = 0.0;
-                c.scal()[S_gov_r_b] = c.par()[P_interest_rate];
-                c.misc()[M_STATUS] = 0;
-            }
-            __syncwarp();
-            phase_firm_decisions(c);
-            phase_fire(c, L.F + L.N);
-            __syncwarp();
-            phase_job_search<ZM>(c);
-            __syncwarp();
-            phase_produce(c);
-            phase_capital_market<ZM>(c);
             if (c.lane == 0) bulk_prefetch_l2(c.blob + L.o_PA, (uint32_t)(L.blob - L.o_PA));
             phase_gov_income(c);
+            KTICK(5);
         }
         __syncthreads();
         mw_goods_market<ZM>(c);
+        KTICK(6);
+        mw_accounting(c);
+        KTICK(7);
         if (c.warp == 0) {
-            phase_accounting(c);
             phase_reward(c);
             __syncwarp();
+            KTICK(8);
             phase_tracking(c);
-            phase_bankrupt(c);
-            phase_closing(c);
+            KTICK(9);
+            const int nbad = bankrupt_replace(c);
+            if (c.lane == 0) mw_iscratch(c)[0] = nbad;
+        }
+        __syncthreads();
+        if (mw_iscratch(c)[0] > 0) bankrupt_release(c, c.tid, 32 * NW);
+        if (c.warp == 0) {
+            bankrupt_terminated(c);
             __syncwarp();
+            KTICK(10);
+            if (c.lane == 0) mw_dscratch(c)[0] = closing_scalars(c);
+        }
+        __syncthreads();
+        {
+            const double share = mw_dscratch(c)[0];
+            if (share > 0.0)
+                for (int h = L.W + c.tid; h < L.H; h += 32 * NW) c.PA(h) = c.PA(h) + share;
+        }
+        if (c.warp == 0) {
+            KTICK(11);
             if (a.stats && c.lane < N_STATS) {
                 const double *s = c.scal();
                 double v;
@@ -367,7 +811,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __g
 }
 
 KernelFn kernel_mw(int mode, int max_z, int nw);   // cats_inst_mw.cu
-int mw_extra_bytes(int nw);
+int mw_extra_bytes(int nw, int F);
 
 }  // namespace cats
 #endif

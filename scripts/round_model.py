@@ -87,11 +87,25 @@ def rounds(order, cand, budget, stock, P, rule, window):
                     for j in range(n):
                         if pend[j] and j not in unc and status[j] == "full" and danger.get(term[j], n) < j:
                             unc.add(j); changed = True
+                if rule == "R4":
+                    unc = set(movers)
+                    danger = {}
+                    for i in sorted(unc):
+                        for s_ in lists[i][pos[i]:]:
+                            danger[s_] = min(danger.get(s_, n), i)
+                    newly = [j for j in range(n) if pend[j] and j not in unc and status[j] == "full" and danger.get(term[j], n) < j]
+                    limit = min(newly) if newly else n
+                    commit = [i for i in range(n) if pend[i] and i < limit and ((status[i] in ("full", "none") and i not in unc)
+                              or (status[i] == "exh" and not danger.get(term[i], n) < i))]
+                    commit += [i for i in range(n) if pend[i] and i >= limit and status[i] == "none"]
                 # a mover is itself certain unless its terminal is endangered by a LOWER uncertain lane
                 def endangered(j):
                     return any(i < j and term[j] in lists[i][pos[i]:] for i in unc if i != j)
-                commit = [i for i in range(n) if pend[i] and status[i] in ("full", "none") and i not in unc]
-                if rule == "R1":
+                if rule != "R4":
+                    commit = [i for i in range(n) if pend[i] and status[i] in ("full", "none") and i not in unc]
+                if rule == "R4":
+                    pass
+                elif rule == "R1":
                     if first < n and status[first] == "exh": commit.append(first)
                 else:
                     commit += [i for i in movers if status[i] == "exh" and not endangered(i)]
@@ -116,8 +130,8 @@ if __name__ == "__main__":
         order, cand, budget, stock, P = premarket(W, F, N, 1, t)
         s_ref, l_ref = sequential(order, cand, budget, stock, P)
         print(f"W={W} F={F} t={t}: buyers={int((budget > 0).sum())} sold-out sellers={int((s_ref == 0).sum())}/{F}")
-        for window in (32, 64, 128, 256):
-            for rule in ("R0", "R1", "R2"):
+        for window in (32, 128, 256):
+            for rule in ("R0", "R2", "R4"):
                 s, l, nr, nc, hist = rounds(order, cand, budget, stock, P, rule, window)
                 ok = np.array_equal(s, s_ref) and np.array_equal(l, l_ref)
                 print(f"  window {window:3d} {rule}: rounds {nr:5d} chunks {nc:4d} rounds/chunk {nr / nc:.2f} exact={ok}")

@@ -19,7 +19,7 @@ void run(const KArgs &a)
 template <int ZM, int NW, int MODE>
 void run_mw(const KArgs &a)
 {
-    simt::launch((unsigned)a.B, 32u * NW, (size_t)a.slice + MWLayout<NW>::bytes, [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE>(a); });
+    simt::launch((unsigned)a.B, 32u * NW, (size_t)a.slice + MWLayout<NW>::total(a.L.F), [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE>(a); });
 }
 
 }  // namespace

@@ -124,7 +124,7 @@ def test_masked_reset_and_episode_stream():
 
 @pytest.mark.parametrize("W,F,N,warps,mode,schedule", [(1000, 100, 20, 4, 2, 0), (1000, 100, 20, 8, 1, 3), (1000, 100, 20, 2, 2, 1),
                                                          (300, 30, 8, 4, 1, 1), (130, 7, 2, 8, 1, 6), (37, 3, 1, 2, 1, 0),
-                                                         (2000, 200, 40, 8, 1, 1)])
+                                                         (2000, 200, 40, 8, 1, 1), (900, 300, 12, 4, 1, 4)])
 def test_multiwarp_kernel_matches_oracle(W, F, N, warps, mode, schedule):
     """cats_period_mw.cuh: one block per economy, `warps` warps, the wide goods market with commit rule R2."""
     B, T = 2, 60

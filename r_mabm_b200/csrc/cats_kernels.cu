@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "cats_period.cuh"
 
@@ -19,22 +20,21 @@ using namespace cats;
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
-static long long *g_cycles = nullptr;  // debug: set by cats_debug_phase_cycles()
-static int g_group = 0;                // debug: set by cats_debug_set_group() (0 = automatic)
-static int g_static = 1;               // debug: cats_debug_set_static(0) keeps the generic kernel for the default size
-static int g_warps = 0;                // debug: cats_debug_set_warps(): warps per economy (0 = chosen per launch)
+static std::atomic<long long *> g_cycles{nullptr};  // test / profiling hook: cats_debug_phase_cycles()
+static std::atomic<int> g_group{0};    // test hook: cats_debug_set_group() (0 = automatic)
+static std::atomic<int> g_static{1};   // test hook: cats_debug_set_static(0) keeps the generic kernel for the default size
+static std::atomic<int> g_warps{0};    // test hook: cats_debug_set_warps(): warps per economy (0 = chosen per launch)
 // development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
 static int smem_pad()
 {
-    static int pad = -1;
-    if (pad < 0) { const char *e = getenv("CATS_SMEM_PAD"); pad = e ? atoi(e) : 0; if (pad < 0) pad = 0; }
+    static const int pad = [] { const char *e = getenv("CATS_SMEM_PAD"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v; }();
     return pad;
 }
 static bool is_default_size(const Layout &L)
 {
-    static int off = -1;   // development aid: CATS_NO_STATIC=1 keeps the generic kernel for every size
-    if (off < 0) { const char *e = getenv("CATS_NO_STATIC"); off = e ? atoi(e) : 0; }
-    return !off && g_static && L.W == DefaultLayout::kW && L.F == DefaultLayout::kF && L.N == DefaultLayout::kN && smem_pad() == 0;
+    // development aid: CATS_NO_STATIC=1 keeps the generic kernel for every size
+    static const int off = [] { const char *e = getenv("CATS_NO_STATIC"); return e ? atoi(e) : 0; }();
+    return !off && g_static.load() && L.W == DefaultLayout::kW && L.F == DefaultLayout::kF && L.N == DefaultLayout::kN && smem_pad() == 0;
 }
 // production: Philox draws, no debug stop, no debug image
 static KernelFn select_kernel(const Layout &L, int max_z, int g, bool masked = false, bool production = true,
@@ -54,9 +54,9 @@ static int slice_bytes(const Layout &L) { return ((L.smem + smem_pad()) + 15) & 
 // wins.  CATS_GROUP=<1|2|4|8|12|14> overrides (development aid).
 static int choose_group(const Layout &L, long long B, int sms)
 {
-    static int env_forced = -1;
-    if (env_forced < 0) { const char *e = getenv("CATS_GROUP"); env_forced = e ? atoi(e) : 0; }
-    const int forced = g_group ? g_group : env_forced;
+    static const int env_forced = [] { const char *e = getenv("CATS_GROUP"); return e ? atoi(e) : 0; }();
+    const int gg = g_group.load();
+    const int forced = gg ? gg : env_forced;
     const int slice = slice_bytes(L);
     const int sm_bytes = 228 * 1024, block_max = 227 * 1024, reserve = 1024;
     const int cand[6] = {14, 12, 8, 4, 2, 1};
@@ -85,9 +85,9 @@ static int choose_group(const Layout &L, long long B, int sms)
 // keep ~28 warps on every SM, if the block's shared memory still lets every economy of the launch be resident.
 static int choose_warps(const Layout &L, long long B, int sms)
 {
-    static int env_forced = -1;
-    if (env_forced < 0) { const char *e = getenv("CATS_WARPS"); env_forced = e ? atoi(e) : 0; }
-    const int forced = g_warps ? g_warps : env_forced;
+    static const int env_forced = [] { const char *e = getenv("CATS_WARPS"); return e ? atoi(e) : 0; }();
+    const int gw = g_warps.load();
+    const int forced = gw ? gw : env_forced;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
     if (sms < 1) sms = 1;
     const long long want = (long long)kMaxPerSM * sms / (B > 0 ? B : 1);
@@ -223,41 +223,72 @@ int cats_tape_offsets(int W, int F, int N, int z_c, int z_k, int z_e, uint64_t o
 }
 
 
-static int configure_smem(KernelFn fn, int smem)
-{
-    int dev = 0, max_optin = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
-    return CATS_OK;
-}
+// ---- launch configuration, cached: the attributes of a kernel have to be set once per (device, kernel, shared-memory
+// size), the device's limits read once per device.  A period of a small batch is ~150 us: setting two function
+// attributes and asking for the occupancy on every call (as round 1 did) is a visible part of it.
+struct DevInfo { int known, sms, max_optin; };
+static DevInfo g_dev[64];
+struct CfgEntry { int dev; KernelFn fn; int smem; int occ; };
+static CfgEntry g_cfg[128];
+static int g_ncfg = 0;
+static std::mutex g_cfg_mutex;
 
-static int configure_kernel(const Layout &L, KernelFn fn, int g, int *blocks_per_sm, int *num_sms)
+static int device_info(int *dev_out, DevInfo *out)
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-    int max_optin = 0;
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int smem = slice_bytes(L) * g;
-    if (smem > max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    if (dev < 0 || dev >= 64) return fail(CATS_ECUDA, "device ordinal out of range%s", "");
+    if (!g_dev[dev].known) {
+        cudaDeviceGetAttribute(&g_dev[dev].max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+        g_dev[dev].known = 1;
+    }
+    *dev_out = dev; *out = g_dev[dev];
+    return CATS_OK;
+}
+
+// sets the kernel up for `smem` bytes of dynamic shared memory (once); *occ (nullable): resident blocks per SM
+static int configure(KernelFn fn, int threads, int smem, int *occ_out, int *sms_out)
+{
+    int dev = 0; DevInfo di;
+    if (int rc = device_info(&dev, &di)) return rc;
+    if (sms_out) *sms_out = di.sms;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        for (int i = 0; i < g_ncfg; ++i)
+            if (g_cfg[i].dev == dev && g_cfg[i].fn == fn && g_cfg[i].smem == smem) { if (occ_out) *occ_out = g_cfg[i].occ; return CATS_OK; }
+    }
+    if (smem > di.max_optin) return fail(CATS_ESMEM, "economy working set exceeds shared memory per block%s", "");
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // the whole unified L1 as shared memory: residency (economies per SM) is what hides latency here,
     // and the streamed tail goes through L2 anyway
     e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads * g, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
     if (e != cudaSuccess) return fail(CATS_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (occ < 1) return fail(CATS_ESMEM, "kernel cannot be resident with this working set%s", "");
+    {
+        // a kernel keeps ONE dynamic-shared-memory limit: entries of the same kernel with another size are stale now
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        int n = 0;
+        for (int i = 0; i < g_ncfg; ++i) if (!(g_cfg[i].dev == dev && g_cfg[i].fn == fn)) g_cfg[n++] = g_cfg[i];
+        g_ncfg = n;
+        if (g_ncfg < 128) g_cfg[g_ncfg++] = CfgEntry{dev, fn, smem, occ};
+    }
+    if (occ_out) *occ_out = occ;
+    return CATS_OK;
+}
+
+static int configure_smem(KernelFn fn, int threads, int smem) { return configure(fn, threads, smem, nullptr, nullptr); }
+
+static int configure_kernel(const Layout &L, KernelFn fn, int g, int *blocks_per_sm, int *num_sms)
+{
+    int occ = 0, sms = 0;
+    if (int rc = configure(fn, kThreads * g, slice_bytes(L) * g, &occ, &sms)) return rc;
     *blocks_per_sm = occ * g; *num_sms = sms;   // economies resident per SM
     return CATS_OK;
 }
@@ -334,10 +365,10 @@ int cats_step(const cats_step_args *s)
 
     KArgs a;
     fill_kargs(s, a);
-    a.cycles = g_cycles;
+    a.cycles = g_cycles.load();
     int occ = 0, sms = 0;
     int dev = 0, nsm = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    { DevInfo di; if (int rc = device_info(&dev, &di)) return rc; nsm = di.sms; }
     a.slice = slice_bytes(a.L);
     a.bars = s->stop_phase ? 0 : 1;
     const bool default_z = s->z_all[0] == DefaultLayout::kZc && s->z_all[1] == DefaultLayout::kZk && s->z_all[2] == DefaultLayout::kZe;
@@ -348,7 +379,7 @@ int cats_step(const cats_step_args *s)
         // one block = one economy, nw warps (cats_period_mw.cuh)
         KernelFn fn = kernel_mw((default_z && is_default_size(a.L)) ? 2 : 1, s->max_z, nw);
         const int smem = a.slice + mw_extra_bytes(nw, a.L.F);
-        if (int rc = configure_smem(fn, smem)) return rc;
+        if (int rc = configure_smem(fn, kThreads * nw, smem)) return rc;
         fn<<<(unsigned)s->B, kThreads * nw, smem, (cudaStream_t)s->stream>>>(a);
     } else {
         const int g = choose_group(a.L, s->B, nsm);

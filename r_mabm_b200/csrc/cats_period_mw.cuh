@@ -41,8 +41,8 @@ template <int NW>
 struct MWLayout {
     static constexpr int T = 32 * NW;
     static constexpr int o_mask = 0;                                 // [2][MW_ROWS][NW] u32: lanes whose terminal hashes to the row
-    static constexpr int o_dang = o_mask + 2 * MW_ROWS * NW * 4;     // [2][MW_ROWS] i32: lowest uncertain lane that may still come here
-    static constexpr int o_d = o_dang + 2 * MW_ROWS * 4;             // [T] f64: what the lane wants at its terminal
+    static constexpr int o_dang = o_mask + 2 * MW_ROWS * NW * 4;     // [MW_ROWS] i32: round stamp << 10 | lowest uncertain lane that may still come here
+    static constexpr int o_d = o_dang + MW_ROWS * 4;                 // [T] f64: what the lane wants at its terminal
     static constexpr int o_term = o_d + T * 8;                       // [T] i32: the lane's terminal (-1: none)
     static constexpr int bytes = (o_term + T * 4 + 15) & ~15;       // then [F] u64: the demand accumulators of the goods market
     static constexpr int total(int F) { return bytes + ((8 * F + 15) & ~15); }
@@ -75,7 +75,10 @@ __device__ void mw_goods_market(C &c)
     enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
     unsigned *maskb = reinterpret_cast<unsigned *>(c.mw + ML::o_mask);
+    // danger table: entries carry the stamp of the round that wrote them.  The stamp counts DOWN, so an atomic min
+    // lets this round's entries win over stale ones and nobody has to clean the table between rounds.
     int *dangb = reinterpret_cast<int *>(c.mw + ML::o_dang);
+    int stamp = 0x1fffff;
     double *sh_d = reinterpret_cast<double *>(c.mw + ML::o_d);   // (block barriers order the accesses)
     volatile int *sh_term = reinterpret_cast<volatile int *>(c.mw + ML::o_term);
     if (warp == 0) {
@@ -90,7 +93,7 @@ __device__ void mw_goods_market(C &c)
         }
     } else ord.k = c.okeys();
     for (int i = tid; i < 2 * MW_ROWS * NW; i += T) maskb[i] = 0u;
-    for (int i = tid; i < 2 * MW_ROWS; i += T) dangb[i] = 0x7fffffff;
+    for (int i = tid; i < MW_ROWS; i += T) dangb[i] = 0x7fffffff;
     for (int f = tid; f < F; f += T) acc[f] = 0ull;
     __syncthreads();
     const int nch = (H + T - 1) / T;
@@ -165,7 +168,10 @@ __device__ void mw_goods_market(C &c)
             if (tid == 0) simt::g_count[0]++;
 #endif
             unsigned *mask = maskb + parity * (MW_ROWS * NW);
-            int *dang = dangb + parity * MW_ROWS;
+            int *dang = dangb;
+            --stamp;
+            // lowest uncertain lane that may still come to the seller of table row r this round (T = nobody)
+            auto danger_at = [&](int r) { const int v = dang[r]; return (v >> 10) == stamp ? (v & 1023) : 0x7fffffff; };
             // ---- walk: to the first seller of the list that has stock, registering demand on the way
             if (pend && term >= 0 && !(mkt.yr[term].x > 0.0)) term = TERM_WALK;   // emptied by a lane that committed
             if (term == TERM_WALK) {
@@ -183,16 +189,30 @@ __device__ void mw_goods_market(C &c)
 #pragma unroll
                         for (int k = 0; k < ZM - 1; ++k) { sl[k] = -1; st[k] = 0.0; if (rest.pop(sl[k])) st[k] = mkt.yr[sl[k]].x; else sl[k] = -1; }
                         term = TERM_NONE;
+                        int nvis = 0;
 #pragma unroll
                         for (int k = 0; k < ZM - 1; ++k) {
                             if (term == TERM_NONE && sl[k] >= 0) {
                                 int dummy;
                                 cl.pop(dummy);
-                                fx_add(&acc[sl[k]], xb);
+                                nvis = k + 1;
                                 if (st[k] > 0.0) term = sl[k];
                             }
                         }
                         if (term >= 0) d_t = b * mkt.yr[term].y;
+                        // demand at the sellers visited: the low words first (independent atomics in flight
+                        // together), then the carries into the high words (see fx_add)
+                        const unsigned lo = (unsigned)xb, hi = (unsigned)(xb >> 32);
+                        unsigned old[ZM - 1];
+#pragma unroll
+                        for (int k = 0; k < ZM - 1; ++k)
+                            if (k < nvis) old[k] = atomicAdd(reinterpret_cast<unsigned *>(&acc[sl[k]]), lo);
+#pragma unroll
+                        for (int k = 0; k < ZM - 1; ++k)
+                            if (k < nvis) {
+                                const unsigned h2 = hi + ((old[k] + lo < old[k]) ? 1u : 0u);
+                                if (h2) atomicAdd(reinterpret_cast<unsigned *>(&acc[sl[k]]) + 1, h2);
+                            }
                     }
                 }
             }
@@ -204,17 +224,23 @@ __device__ void mw_goods_market(C &c)
             __syncthreads();
             MWTICK(13);
             // ---- replay the lower lanes at my terminal, in lane order
-            int status = ST_IDLE;
+            int status = ST_IDLE, nxt = 0x7fffffff;
             double ys = 0.0;
             if (has) {
                 ys = mkt.yr[term].x;
                 bool sold = false;
                 unsigned mw_[NW];
 #pragma unroll
-                for (int w2 = 0; w2 < NW; ++w2) mw_[w2] = w2 < warp ? mask[row * NW + w2] : (w2 == warp ? mask[row * NW + w2] & lt : 0u);
+                for (int w2 = 0; w2 < NW; ++w2) mw_[w2] = mask[row * NW + w2];
+                // (exact rows) the next lane above me at this seller: the last lane that commits writes the stock
+#pragma unroll
+                for (int w2 = NW - 1; w2 >= 0; --w2) {
+                    const unsigned up = w2 > warp ? mw_[w2] : (w2 == warp ? mw_[w2] & ~(lt | (1u << lane)) : 0u);
+                    if (up) nxt = w2 * 32 + __ffs(up) - 1;
+                }
 #pragma unroll
                 for (int w2 = 0; w2 < NW; ++w2) {
-                    unsigned m = mw_[w2];
+                    unsigned m = w2 < warp ? mw_[w2] : (w2 == warp ? mw_[w2] & lt : 0u);
                     if (exact_rows) {
                         while (m && !sold) {   // two peers' demands in flight per step
                             const int p0 = w2 * 32 + __ffs(m) - 1; m &= m - 1;
@@ -238,17 +264,16 @@ __device__ void mw_goods_market(C &c)
                 status = sold ? ST_SOLD : (ys > d_t ? ST_FULL : ST_EXHAUST);
             }
             // ---- who is uncertain, which sellers are in danger (closed by iteration)
-            bool unc = status >= ST_EXHAUST, published = false;
+            bool unc = status >= ST_EXHAUST;
             auto publish = [&]() {
                 auto rest = cl;
                 int s;
-                while (rest.pop(s)) atomicMin(&dang[s & (MW_ROWS - 1)], tid);
-                published = true;
+                while (rest.pop(s)) atomicMin(&dang[s & (MW_ROWS - 1)], (stamp << 10) | tid);
             };
             if (unc) publish();
             if (__syncthreads_or(unc)) {
                 while (true) {
-                    const bool newly = status == ST_FULL && !unc && dang[row] < tid;
+                    const bool newly = status == ST_FULL && !unc && danger_at(row) < tid;
                     if (newly) { unc = true; publish(); }
 #ifdef CATS_EMU_COUNT
                     if (tid == 0) simt::g_count[1]++;
@@ -258,23 +283,23 @@ __device__ void mw_goods_market(C &c)
             }
             MWTICK(14);
             // ---- commit
+            // The committed lanes at a seller are a prefix of its queue.  Exact rows: the last of them -- the lane
+            // whose next peer is endangered, or has none -- stores the stock; hashed rows: an atomic min over them.
+            const int dmin = status == ST_FULL || status == ST_EXHAUST ? danger_at(row) : 0x7fffffff;
             if (status == ST_FULL && !unc) {
-                atomicMin(reinterpret_cast<unsigned long long *>(&mkt.yr[term].x), (unsigned long long)__double_as_longlong(ys - d_t));
+                if (!exact_rows)
+                    atomicMin(reinterpret_cast<unsigned long long *>(&mkt.yr[term].x), (unsigned long long)__double_as_longlong(ys - d_t));
+                else if (nxt == 0x7fffffff || dmin < nxt) mkt.yr[term].x = ys - d_t;
                 b = 0.0; pend = false;
-            } else if (status == ST_EXHAUST && !(dang[row] < tid)) {
+            } else if (status == ST_EXHAUST && !(dmin < tid)) {
                 b = b - ys * mkt.p[term];
-                atomicMin(reinterpret_cast<unsigned long long *>(&mkt.yr[term].x), 0ull);
+                if (!exact_rows) atomicMin(reinterpret_cast<unsigned long long *>(&mkt.yr[term].x), 0ull);
+                else mkt.yr[term].x = 0.0;
                 if (b > 0.0) { term = TERM_WALK; xb = fx_from(b * rpavg); } else { term = TERM_NONE; pend = false; }
             }
             any = __syncthreads_or(pend);
             // ---- leave this round's tables clean (they are used again two rounds from now)
             if (has) mask[row * NW + warp] = 0u;
-            if (published) {
-                auto rest = cl;
-                int s;
-                // the list as it was when it was published: a lane that just exhausted its seller has not walked yet
-                while (rest.pop(s)) dang[s & (MW_ROWS - 1)] = 0x7fffffff;
-            }
             parity ^= 1;
             MWTICK(15);
         }

@@ -374,6 +374,36 @@ def run_b200(args):
     all_stats = sh.gather(last_stats)
     un_mean = float(all_stats[:, 0, nat.STAT_NAMES.index("Un")].mean())
 
+    # The other scaling mode beside it (N > 1, heuristic configs): the driver's line is the BASELINE-named strong
+    # split; the same command also measures `economies` PER GPU (weak), shorter, so that both sit in one record.
+    also = None
+    if world > 1 and not cfg["rollout"]:
+        other = "weak" if args.scaling == "strong" else "strong"
+        total2 = base * world if other == "weak" else base
+        flush_buf = None                                     # give the 256 MB back
+        sh2 = ShardedCats(total2, rank=rank, world=world, device=dev, W=W, F=F, N=N, n_agents=nA, seed=20260119)
+        env2, B2 = sh2.env, sh2.env.B
+        env2.run(args.burnin)
+        a2 = torch.ones((B2, nA, 2), dtype=torch.float64, device=dev)
+        m2 = torch.zeros((B2, nA), dtype=torch.uint8, device=dev)
+        fl2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if B2 * env2.blob_bytes < 1.2 * L2_BYTES else None
+        n2 = max(20, min(args.steps, 100))
+        for _ in range(5):
+            env2.step(a2, m2, want_stats=True)
+        barrier()
+        s2 = [torch.cuda.Event(enable_timing=True) for _ in range(n2)]
+        e2 = [torch.cuda.Event(enable_timing=True) for _ in range(n2)]
+        for i in range(n2):
+            if fl2 is not None:
+                fl2.zero_()
+            s2[i].record(); env2.step(a2, m2, want_stats=True); e2[i].record()
+        barrier()
+        t2 = torch.tensor([sum(s2[i].elapsed_time(e2[i]) for i in range(n2))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        also = {"scaling": other, "economies_total": total2, "economies_per_gpu": B2, "steps": n2,
+                "value": total2 * n2 / (float(t2[0]) * 1e-3), "unit": UNIT,
+                "l2_flush_between_steps": fl2 is not None}
+
     if rank == 0:
         value = total * args.steps / (total_ms * 1e-3)
         peak, peak_src = measured_peak_hbm()
@@ -416,6 +446,8 @@ def run_b200(args):
                                  "markets, not by bandwidth; see DESIGN.md 2.3"},
             "clocks": clocks, "launch": env.launch_info(), "mean_unemployment_check": un_mean,
         }
+        if also is not None:
+            line["also_measured"] = also
         if not args.no_cpu_baseline and world == 1:        # reported at N = 1 only (the host cores are busy driving N ranks otherwise)
             cb = cpu_baseline(cfg, args.burnin)
             line["cpu_baseline"] = cb

@@ -91,8 +91,9 @@ static int choose_warps(const Layout &L, long long B, int sms)
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
     if (sms < 1) sms = 1;
     const long long want = (long long)kMaxPerSM * sms / (B > 0 ? B : 1);
-    const int cand[3] = {8, 4, 2};
-    for (int i = 0; i < 3; ++i) {
+    // two warps per economy never paid off in the measurements: four or eight, or the one-warp kernel
+    const int cand[2] = {8, 4};
+    for (int i = 0; i < 2; ++i) {
         const int nw = cand[i];
         if (want < nw) continue;
         const long long bytes = slice_bytes(L) + mw_extra_bytes(nw, L.F) + 1024;

@@ -14,9 +14,9 @@
 //   - matching markets (job search, capital goods, consumption goods): 32 agents in visiting order
 //     are prepared in parallel (visiting order, Philox candidate draws, price sort in registers) and
 //     committed in rounds: every lane walks its candidate list against the current seller table,
-//     lanes that meet at one seller replay each other's demands in lane order (shuffles), and the
-//     longest prefix of lanes whose outcome cannot depend on an uncommitted one is committed at
-//     once.  A round ends at the first buyer that exhausts a seller; the outcome is exactly the
+//     lanes that meet at one seller replay each other's demands in lane order (shuffles), and every
+//     lane whose outcome cannot depend on an uncommitted lower lane is committed at once -- also past
+//     a seller that sells out (rule R2, see phase_goods_market); the outcome is exactly the
 //     sequential visiting-order market of the reference, including the order of every fp64 add.
 //   - the warps of a block exchange no data; block barriers only re-align them (once per period and
 //     once before the closing phases).
@@ -833,6 +833,20 @@ template <> struct CandList<false> {
         w0 = (w0 >> 16) | (w1 << 48); w1 >>= 16;
         return true;
     }
+    // lane `src`'s list (warp collective)
+    __device__ __forceinline__ CandList from_lane(int src) const
+    {
+        CandList r;
+        r.w0 = __shfl_sync(FULL, w0, src); r.w1 = __shfl_sync(FULL, w1, src);
+        return r;
+    }
+    // is `seller` still on the list?  (a zero 16-bit slot of list ^ splat(seller + 1); empty slots are 0 and never match)
+    __device__ __forceinline__ bool contains(int seller) const
+    {
+        const unsigned long long x = (unsigned long long)(unsigned)(seller + 1) * 0x0001000100010001ull;
+        const unsigned long long a = w0 ^ x, b = w1 ^ x;
+        return ((((a - 0x0001000100010001ull) & ~a) | ((b - 0x0001000100010001ull) & ~b)) & 0x8000800080008000ull) != 0ull;
+    }
 };
 template <> struct CandList<true> {
     unsigned w0 = 0u, w1 = 0u;
@@ -849,6 +863,18 @@ template <> struct CandList<true> {
         w0 = __funnelshift_r(w0, w1, 8); w1 >>= 8;
         return true;
     }
+    __device__ __forceinline__ CandList from_lane(int src) const
+    {
+        CandList r;
+        r.w0 = __shfl_sync(FULL, w0, src); r.w1 = __shfl_sync(FULL, w1, src);
+        return r;
+    }
+    __device__ __forceinline__ bool contains(int seller) const
+    {
+        const unsigned x = (unsigned)(seller + 1) * 0x01010101u;
+        const unsigned a = w0 ^ x, b = w1 ^ x;
+        return ((((a - 0x01010101u) & ~a) | ((b - 0x01010101u) & ~b)) & 0x80808080u) != 0u;
+    }
 };
 
 // a14 + a15 + a16: workers_get_paid!, households_find_cons_budget!, consumption_goods_market!
@@ -858,10 +884,14 @@ template <> struct CandList<true> {
 //   commit (rounds): every "dirty" lane walks down its sorted candidates: at each seller it
 //       registers its demand b / P (fixed-point atomic add: order-free) and stops at the first one
 //       with stock, its terminal.  Lanes with the same terminal replay the purchases of the lower
-//       lanes in lane order (shuffles), so each knows the stock it will find.  Everything up to and
-//       including the first lane that exhausts its seller is committed; that lane (with what is left
-//       of its budget) and the lanes queued behind it at the exhausted seller walk on in the next
-//       round.  Stock, sales and budgets therefore follow the visiting order exactly.
+//       lanes in lane order (shuffles), so each knows the stock it will find.  A lane that exhausts its
+//       seller (it takes what is left and keeps the rest of its budget) or finds it sold out walks on
+//       in the next round -- to a seller still on its list.  Rule R2: a lane commits unless its terminal
+//       is on the remaining list of such a lane BELOW it (then the stock it replayed is not final;
+//       if it is a full buyer its own list endangers the lanes above it in turn: closed by iteration
+//       over the uncertain lanes, two shuffles each).  Round 1 stopped every round at the first
+//       sell-out: ~100 rounds per period at the default size; R2 needs ~67 (scripts/round_model.py).
+//       Stock, sales and budgets follow the visiting order exactly.
 template <int ZM, class C>
 __device__ void phase_goods_market(C &c)
 {
@@ -986,20 +1016,36 @@ __device__ void phase_goods_market(C &c)
             double ys = 0.0;
             if (has) ys = mkt.yr[term].x;
             bool sold = false;
+            int esrc = 0;   // the lane that empties my seller before my turn (if sold)
             while (__any_sync(FULL, rem != 0u)) {
                 const int src = __ffs(rem) - 1;   // -1 (no peer left) reads lane 31: the value is not used then
                 const double di = __shfl_sync(FULL, d_t, src);
                 if (rem) {
                     rem &= rem - 1;
-                    if (ys > di) ys = ys - di; else { sold = true; rem = 0u; }   // sold out before my turn: stop replaying
+                    if (ys > di) ys = ys - di; else { sold = true; esrc = src; rem = 0u; }   // sold out before my turn: stop replaying
                 }
             }
             const bool full = has && !sold && ys > d_t;
-            const unsigned so = __ballot_sync(FULL, has && !sold && !full);   // lanes that exhaust their seller
-            const int s = so ? __ffs(so) - 1 : 31;
-            const unsigned commit = pend & ((2u << s) - 1u);   // lanes 0..s (s == 31: all, 2u << 31 wraps to 0)
+            // ---- who may commit (rule R2, cats_period_mw.cuh): a lane that exhausts its seller or finds it sold out
+            // walks on -- to one of the sellers left on its list; lanes above it whose terminal is on that list
+            // cannot be sure of the stock they replayed (and if they buy there in full they are uncertain in turn:
+            // their lists count too).  Everybody else commits, also past a seller that sells out.
+            const unsigned movers = __ballot_sync(FULL, has && (sold || !full));
+            bool endangered = false;
+            if (movers) {
+                unsigned todo = movers, unc = movers;
+                while (todo) {
+                    const int i = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const auto li = cl.from_lane(i);
+                    const bool hit = has && !sold && lane > i && li.contains(term);
+                    endangered |= hit;
+                    const unsigned newly = __ballot_sync(FULL, hit && full) & ~unc;
+                    unc |= newly; todo |= newly;
+                }
+            }
+            const unsigned commit = __ballot_sync(FULL, mine && (!has || (!sold && !endangered)));
             const bool cm = (commit >> lane) & 1u;
-            const int xs = __shfl_sync(FULL, term, s);   // the seller exhausted by lane s (if so != 0)
             bool done = false;
             if (cm) {
                 if (!has) done = true;                    // nothing left to visit: the rest of b is saved
@@ -1007,7 +1053,7 @@ __device__ void phase_goods_market(C &c)
                     const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
                     const int seller = term;
                     if (full) { ys = ys - d_t; b = 0.0; done = true; }
-                    else {                                 // lane s: partial fill, then walk on
+                    else {                                 // takes what is left, then walks on
                         b = b - ys * mkt.p[seller]; ys = 0.0;
                         term = b > 0.0 ? TERM_WALK : TERM_NONE;
                         done = term == TERM_NONE;
@@ -1015,8 +1061,8 @@ __device__ void phase_goods_market(C &c)
                     }
                     if (lastp) mkt.yr[seller].x = ys;
                 }
-            } else if (mine && so && has && term == xs) {
-                term = TERM_WALK;                          // queued behind lane s at the exhausted seller
+            } else if (sold && ((commit >> esrc) & 1u)) {
+                term = TERM_WALK;                          // queued behind a lane that emptied the seller for good
             }
             pend &= ~__ballot_sync(FULL, done);
             __syncwarp();

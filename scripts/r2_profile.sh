@@ -1,0 +1,24 @@
+# round-2 ncu captures (one gpurun call, one GPU).  Each command runs plain first, then under ncu.
+set -x
+O=gpurun_out
+NCU="ncu --clock-control none"
+# 1. launch lists: the bench command (config 3) and the MARL rollout (config 4)
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/r02_plain_bench.log 2>&1 &&
+$NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/r02_ncu_bench.log 2>&1
+python scripts/r2_ncu_target.py rollout 4096 10 > $O/r02_plain_rollout.log 2>&1 &&
+$NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/r02_launches_rollout.csv python scripts/r2_ncu_target.py rollout 4096 10 > $O/r02_ncu_rollout.log 2>&1
+# 2. --set full, one launch each
+full() {  # name, kernel regex, skip, target args...
+  name=$1; rx=$2; skip=$3; shift 3
+  python scripts/r2_ncu_target.py "$@" > $O/r02_plain_$name.log 2>&1 &&
+  $NCU --set full --import-source on -k regex:$rx -s $skip -c 1 -f -o $O/prof_r02_$name python scripts/r2_ncu_target.py "$@" > $O/r02_ncufull_$name.log 2>&1
+  echo "$name rc=$?"
+}
+full c3 cats_period_kernel 1 period 16384 1 1000 100 20 1
+full c2mw cats_period_mw_kernel 1 period 1024 1 1000 100 20 0
+full c5mw cats_period_mw_kernel 1 period 256 1 10000 1000 200 0
+full c5one cats_period_kernel 1 period 256 1 10000 1000 200 1
+full tape cats_period_kernel 1 tape 1024
+full q cats_q_kernel 5 rollout 4096 10
+full init cats_init_kernel 0 period 16384 1 1000 100 20 1
+ls -la $O/*.ncu-rep

@@ -125,12 +125,15 @@ def rounds(order, cand, budget, stock, P, rule, window):
     return stock, left, n_rounds, n_chunks, committed_hist
 
 
+WINDOWS = tuple(int(x) for x in sys.argv[1:]) or (32, 128, 256)
+
+
 if __name__ == "__main__":
     for (W, F, N, t) in ((1000, 100, 20, 320), (1000, 100, 20, 350), (10000, 1000, 200, 120)):
         order, cand, budget, stock, P = premarket(W, F, N, 1, t)
         s_ref, l_ref = sequential(order, cand, budget, stock, P)
         print(f"W={W} F={F} t={t}: buyers={int((budget > 0).sum())} sold-out sellers={int((s_ref == 0).sum())}/{F}")
-        for window in (32, 128, 256):
+        for window in WINDOWS:
             for rule in ("R0", "R2", "R4"):
                 s, l, nr, nc, hist = rounds(order, cand, budget, stock, P, rule, window)
                 ok = np.array_equal(s, s_ref) and np.array_equal(l, l_ref)

@@ -77,10 +77,12 @@ def parse():
 
 
 def source_hash() -> str:
-    """Hash of the kernel sources the loaded library was built from (ties profiles/roofline_traffic.json to a build)."""
+    """Hash of the sources (and build flags) of the kernel bench.py times at config 3 -- the default-configuration
+    one-warp kernel -- to tie profiles/roofline_traffic.json (an ncu capture) to the build that is running."""
     h = hashlib.sha1()
-    for p in sorted((ROOT / "r_mabm_b200" / "csrc").glob("*.cu*")) + sorted((ROOT / "r_mabm_b200" / "csrc").glob("*.h")):
-        h.update(p.name.encode()); h.update(p.read_bytes())
+    csrc = ROOT / "r_mabm_b200" / "csrc"
+    for name in ("cats_period.cuh", "cats_device.cuh", "cats_layout.h", "cats_inst_static.cu", "build.sh"):
+        h.update(name.encode()); h.update((csrc / name).read_bytes())
     return h.hexdigest()[:16]
 
 

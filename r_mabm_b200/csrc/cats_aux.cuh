@@ -19,7 +19,8 @@ __global__ void cats_init_kernel(unsigned char *blobs, long long B, Layout L, co
     __syncthreads();
     const double *par = params + (params_stride ? (size_t)b * (size_t)params_stride : 0);
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < L.blob / 8; i += nt) reinterpret_cast<double *>(blob)[i] = 0.0;
+    // blobs are multiples of 128 bytes and 128-byte aligned: 16-byte stores
+    for (int i = tid; i < L.blob / 16; i += nt) reinterpret_cast<uint4 *>(blob)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const double P0 = 3.0, PK0 = 3.0, K0 = 10.0, LIQ0 = 10.0, YC0 = 5.0, YK0 = 3.0, PA0 = 2.0;
     double *scal = reinterpret_cast<double *>(blob + L.o_scal);

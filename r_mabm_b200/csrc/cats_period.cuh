@@ -364,6 +364,9 @@ __device__ __forceinline__ void fire_oversize(C &c, int f)
 {
     const int W = c.layout().W, lane = c.lane;
     const int s = -c.vac()[f];
+#ifdef CATS_EMU_COUNT
+    if (lane == 0) simt::g_count[2]++;
+#endif
     for (int r = 0; r < s; ++r) {
         unsigned bk = 0xffffffffu; int bw = 0x7fffffff;
         for (int w = lane; w < W; w += 32) {

@@ -1,7 +1,13 @@
-"""profiles/<round>_ncu_period_kernel.md + roofline_traffic.json from an ncu --set full capture.
-usage: make_profile_md.py <rep> <so> <kernel-substring> <economy-periods in the launch> <round tag>"""
+"""profiles/<round>_ncu_<name>.md (+ roofline_traffic.json for the bench kernel) from an ncu --set full capture.
+usage: make_profile_md.py <rep> <so> <kernel-substring> <units in the launch> <round tag> [name [what [unit]]]
+  name: file suffix (default period_kernel: also writes profiles/roofline_traffic.json, tied to the kernel sources by hash)
+  what: one line describing the launch;  unit: what a "unit" is (default economy-period)"""
 import csv, json, re, subprocess, sys
+sys.path.insert(0, ".")
 rep, so, kern, nep, tag = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4]), sys.argv[5]
+name = sys.argv[6] if len(sys.argv) > 6 else "period_kernel"
+what = sys.argv[7] if len(sys.argv) > 7 else f"{int(nep)} default-size economies, ONE period, after the 300-period burn-in."
+unit = sys.argv[8] if len(sys.argv) > 8 else "economy-period"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h, u, r = rows[0], rows[1], rows[2]
@@ -23,25 +29,28 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 dur_us = f("gpu__time_duration.sum") * {"us": 1, "ms": 1e3, "ns": 1e-3, "second": 1e6}[m["gpu__time_duration.sum"][1]]
 dr, dw = unit_bytes("dram__bytes_read.sum"), unit_bytes("dram__bytes_write.sum")
 inst = f("smsp__inst_executed.sum")
-out = [f"# ncu --set full: {kern}, {tag}", "",
-       "Command (gpurun, 1 B200, directly after the same command exited 0 without ncu):", "",
-       "    ncu --set full --clock-control none --import-source on -k regex:cats_period -s 1 -c 1 \\",
-       f"        -o gpurun_out/prof_{tag} python scripts/ncu_target.py {int(nep)} 1", "",
-       f"Launch profiled: {int(nep)} default-size economies, ONE period, after the 300-period burn-in.",
+out = [f"# ncu --set full: {name} ({kern}), {tag}", "",
+       "Capture: scripts/r2_profile.sh (gpurun, 1 B200, each command directly after the same command exited 0 without ncu;",
+       "`ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1`).", "",
+       f"Launch profiled: {what}",
        "Times under ncu are cold-cache and serialised: use shares, not absolutes.", "", "| metric | value |", "|---|---|"]
 for n in want:
     if n in m: out.append(f"| {n} | {m[n][0]} {m[n][1]} |")
-out += [f"| warp instructions per economy-period | {inst / nep:.0f} |",
-        f"| DRAM bytes per economy-period (read + write) | {(dr + dw) / nep:.0f} |",
-        f"| economy-periods/s under ncu | {nep / (dur_us * 1e-6):.3e} |", "",
+out += [f"| warp instructions per {unit} | {inst / nep:.0f} |",
+        f"| DRAM bytes per {unit} (read + write) | {(dr + dw) / nep:.0f} |",
+        f"| {unit}s/s under ncu | {nep / (dur_us * 1e-6):.3e} |", f"| achieved DRAM GB/s under ncu (read + write) | {(dr + dw) / (dur_us * 1e-6) / 1e9:.0f} |", "",
         "Stall reasons (cycles per issued instruction, per warp):", "", "| reason | cycles |", "|---|---|"]
 st = [(float(r[i]), n) for i, n in enumerate(h) if re.fullmatch(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio", n)]
 for v, n in sorted(st, reverse=True):
     if v >= 0.005: out.append(f"| {n.split('stalled_')[1].split('_per_issue')[0]} | {v:.2f} |")
 by = subprocess.run([sys.executable, "scripts/ncu_stalls_by_region.py", rep, so, kern, str(nep)], capture_output=True, text=True).stdout
-out += ["", "Per source function (instructions per economy-period, share of stall samples, stall mix in % of all samples):", "", "```", by.rstrip(), "```"]
-open(f"profiles/{tag}_ncu_period_kernel.md", "w").write("\n".join(out) + "\n")
+out += ["", f"Per source function (instructions per {unit}, share of stall samples, stall mix in % of all samples):", "", "```", by.rstrip(), "```"]
+open(f"profiles/{tag}_ncu_{name}.md", "w").write("\n".join(out) + "\n")
+if name != "period_kernel":
+    print("\n".join(out[:40])); sys.exit(0)
+from bench import source_hash
 json.dump({"kernel": kern, "source": f"profiles/{tag}_ncu_period_kernel.md (ncu --set full, {int(nep)} economies x 1 period)",
+           "source_hash": source_hash(),
            "dram_bytes_read": dr, "dram_bytes_write": dw, "economy_periods": nep,
            "dram_bytes_per_economy_period": (dr + dw) / nep,
            "warp_instructions_per_economy_period": inst / nep,

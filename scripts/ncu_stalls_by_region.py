@@ -20,7 +20,7 @@ def regions(path):
         if m and not l.strip().startswith("//"): out.append((i, m.group(1)))
     return out
 src_dir = "/root/repo/r_mabm_b200/csrc"
-regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_period.cuh", "cats_device.cuh")}
+regs = {f: regions(os.path.join(src_dir, f)) for f in ("cats_kernels.cu", "cats_period.cuh", "cats_period_mw.cuh", "cats_aux.cuh", "cats_device.cuh")}
 def region(key):
     if key is None: return "?"
     f, line = key

@@ -87,6 +87,14 @@ def rounds(order, cand, budget, stock, P, rule, window):
                     for j in range(n):
                         if pend[j] and j not in unc and status[j] == "full" and danger.get(term[j], n) < j:
                             unc.add(j); changed = True
+                if rule == "R3":
+                    # no mover analysis at all: a lane commits unless its terminal is on the remaining list of ANY lower pending lane
+                    danger = {}
+                    for i in range(n):
+                        if pend[i] and term[i] is not None and term[i] >= 0:
+                            for s_ in lists[i][pos[i]:]:
+                                danger[s_] = min(danger.get(s_, n), i)
+                    commit = [i for i in range(n) if pend[i] and (status[i] == "none" or (status[i] in ("full", "exh") and not danger.get(term[i], n) < i))]
                 if rule == "R4":
                     unc = set(movers)
                     danger = {}
@@ -101,9 +109,9 @@ def rounds(order, cand, budget, stock, P, rule, window):
                 # a mover is itself certain unless its terminal is endangered by a LOWER uncertain lane
                 def endangered(j):
                     return any(i < j and term[j] in lists[i][pos[i]:] for i in unc if i != j)
-                if rule != "R4":
+                if rule not in ("R4", "R3"):
                     commit = [i for i in range(n) if pend[i] and status[i] in ("full", "none") and i not in unc]
-                if rule == "R4":
+                if rule in ("R4", "R3"):
                     pass
                 elif rule == "R1":
                     if first < n and status[first] == "exh": commit.append(first)
@@ -134,7 +142,7 @@ if __name__ == "__main__":
         s_ref, l_ref = sequential(order, cand, budget, stock, P)
         print(f"W={W} F={F} t={t}: buyers={int((budget > 0).sum())} sold-out sellers={int((s_ref == 0).sum())}/{F}")
         for window in WINDOWS:
-            for rule in ("R0", "R2", "R4"):
+            for rule in ("R2", "R3"):
                 s, l, nr, nc, hist = rounds(order, cand, budget, stock, P, rule, window)
                 ok = np.array_equal(s, s_ref) and np.array_equal(l, l_ref)
                 print(f"  window {window:3d} {rule}: rounds {nr:5d} chunks {nc:4d} rounds/chunk {nr / nc:.2f} exact={ok}")

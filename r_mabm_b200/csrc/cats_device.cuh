@@ -407,6 +407,7 @@ __device__ __forceinline__ int d2count(double x)
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier
 #ifdef CATS_EMU
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_inval(uint64_t *) {}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { simt::mbar_arrive(bar); }
 __device__ __forceinline__ void fence_mbar_init() {}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t) { simt::mbar_arrive(bar); }
@@ -429,22 +430,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// an mbarrier object has to be invalidated before its memory is used for anything else (or initialised again)
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// has the phase with this parity completed?  (no labels in the PTX: may be inlined any number of times)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_test(bar, parity)) { }
 }
 // producer-side wait: poll with a sleep so that the spinning warp does not steal issue slots
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)

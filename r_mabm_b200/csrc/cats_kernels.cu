@@ -24,6 +24,7 @@ static std::atomic<long long *> g_cycles{nullptr};  // test / profiling hook: ca
 static std::atomic<int> g_group{0};    // test hook: cats_debug_set_group() (0 = automatic)
 static std::atomic<int> g_static{1};   // test hook: cats_debug_set_static(0) keeps the generic kernel for the default size
 static std::atomic<int> g_warps{0};    // test hook: cats_debug_set_warps(): warps per economy (0 = chosen per launch)
+static std::atomic<int> g_pipe{-1};    // test hook: cats_debug_set_pipe(): goods market of the multi-warp kernel (-1 = chosen per launch)
 // development aid: CATS_SMEM_PAD=<bytes> pads the dynamic shared memory of every launch (caps residency)
 static int smem_pad()
 {
@@ -83,6 +84,16 @@ static int choose_group(const Layout &L, long long B, int sms)
 // Warps per economy.  The one-warp kernel fills the GPU from about 28 x SMs economies up; a smaller launch takes as
 // long as ONE economy's dependent chain, so several warps share an economy instead (cats_period_mw.cuh): as many as
 // keep ~28 warps on every SM, if the block's shared memory still lets every economy of the launch be resident.
+// the multi-warp kernel's goods market: a pipeline (producer warps prepare, one warp commits with the one-warp
+// kernel's rounds) where sellers are few, the block-wide market (cats_period_mw.cuh) where they are many
+// (measured, DESIGN.md 2.7: 1,024 default-size economies at 4 warps: pipeline 7.99e6, block-wide 7.41e6; one economy
+// per SM at 8 warps: block-wide 99.8 us, pipeline 104.7 us; 10x economy: no difference)
+static bool choose_pipe(const Layout &L, int nw)
+{
+    const int forced = g_pipe.load();
+    return forced >= 0 ? forced != 0 : (L.F <= 256 && nw <= 4);
+}
+
 static int choose_warps(const Layout &L, long long B, int sms)
 {
     static const int env_forced = [] { const char *e = getenv("CATS_WARPS"); return e ? atoi(e) : 0; }();
@@ -91,7 +102,7 @@ static int choose_warps(const Layout &L, long long B, int sms)
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
     if (sms < 1) sms = 1;
     const long long want = (long long)kMaxPerSM * sms / (B > 0 ? B : 1);
-    // two warps per economy never paid off in the measurements: four or eight, or the one-warp kernel
+    // two warps per economy never paid off, with either goods market: four or eight, or the one-warp kernel
     const int cand[2] = {8, 4};
     for (int i = 0; i < 2; ++i) {
         const int nw = cand[i];
@@ -142,6 +153,7 @@ void cats_debug_set_group(int economies_per_block) { g_group = economies_per_blo
 
 void cats_debug_set_static(int on) { g_static = on ? 1 : 0; }
 void cats_debug_set_warps(int warps_per_economy) { g_warps = warps_per_economy; }
+void cats_debug_set_pipe(int mode) { g_pipe = mode; }
 
 size_t cats_blob_bytes(int W, int F, int N)
 {
@@ -378,7 +390,7 @@ int cats_step(const cats_step_args *s)
     const int nw = (production && !strict && !s->d_active) ? choose_warps(a.L, s->B, nsm) : 1;
     if (nw > 1) {
         // one block = one economy, nw warps (cats_period_mw.cuh)
-        KernelFn fn = kernel_mw((default_z && is_default_size(a.L)) ? 2 : 1, s->max_z, nw);
+        KernelFn fn = kernel_mw((default_z && is_default_size(a.L)) ? 2 : 1, s->max_z, nw, choose_pipe(a.L, nw));
         const int smem = a.slice + mw_extra_bytes(nw, a.L.F);
         if (int rc = configure_smem(fn, kThreads * nw, smem)) return rc;
         fn<<<(unsigned)s->B, kThreads * nw, smem, (cudaStream_t)s->stream>>>(a);

@@ -895,30 +895,77 @@ template <> struct CandList<true> {
 //       over the uncertain lanes, two shuffles each).  Round 1 stopped every round at the first
 //       sell-out: ~100 rounds per period at the default size; R2 needs ~67 (scripts/round_model.py).
 //       Stock, sales and budgets follow the visiting order exactly.
+enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };   // goods-market constants (c.gk())
+
+// the market constants: computed once by ONE thread, parked in shared memory and re-read per chunk
+template <class C>
+__device__ __forceinline__ void goods_constants(C &c)
+{
+    volatile double *gk = c.gk();
+    const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
+    const double xi = c.par()[P_xi];
+    const double net = wb * (1.0 - c.par()[P_tax_rate]);
+    const double rp = 1.0 / price;
+    gk[G_net] = net; gk[G_sub] = sub;
+    gk[G_ir_emp] = C::kStrict ? net / price : net * rp; gk[G_ir_un] = C::kStrict ? sub / price : sub * rp;
+    gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = rp;
+}
+
+template <class C> using GoodsList = CandList<C::kStatic && DefaultLayout::kF <= 254>;
+
+// prepare (one lane = one household h; h < 0: none): a14 + a15 income, permanent income, consumption budget, then
+// a16 the z_c candidates, sorted by price, packed.  pa: wealth in, wealth less the budget out.
+template <int ZM, class C>
+__device__ __forceinline__ void goods_prepare(C &c, const Mkt &mkt, int z, int h, int oc, double dinc, double &pa, double pm,
+                                              double &b, GoodsList<C> &cl)
+{
+    const auto &L = c.layout();
+    const int W = L.W, F = L.F;
+    volatile double *gk = c.gk();
+    b = 0.0;
+    const double rpavg = gk[G_rpavg];
+    if (h >= 0) {
+        const double price = gk[G_price];
+        double ir;
+        if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
+        else ir = C::kStrict ? dinc / price : dinc * rpavg;
+        pm = pm * gk[G_xi] + gk[G_omxi] * ir;
+        const double target = pm + (C::kStrict ? (gk[G_chi] * pa) / price : (gk[G_chi] * pa) * rpavg);
+        b = target * price;
+        if (b > pa) b = pa;
+        if (!(b > 0.0)) b = 0.0;
+        pa = pa - b;
+        c.perm(h) = pm;
+    }
+    if (b > 0.0) {
+        int cand[ZM]; unsigned key[ZM];
+        c.d.template candidates<ZM>(PH_GOODS, h, F, z, cand);
+        // key = price class (14 bits) | draw index (3 bits) | seller (14 bits): F <= 16383
+#pragma unroll
+        for (int k = 0; k < ZM; ++k)
+            key[k] = k < z ? (mkt.cls[cand[k]] << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
+        sort_keys<ZM>(key);
+#pragma unroll
+        for (int k = 0; k < ZM; ++k)
+            if (k < z) cl.set(k, key[k] & 0x3fffu);
+    }
+}
+
+template <int ZM, class C>
+__device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long long *acc, int h, double pa, double b, GoodsList<C> cl);
+
 template <int ZM, class C>
 __device__ void phase_goods_market(C &c)
 {
     const auto &L = c.layout();
     const int W = L.W, F = L.F, H = L.H, lane = c.lane;
-    const unsigned lt = c.lt();
     const int z = c.z_c() < F ? c.z_c() : F;
     Mkt mkt(c.sm + L.s_U, F);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
     OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
-    // market constants: computed once, parked in shared memory and re-read per chunk (registers)
-    enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
-    if (lane == 0) {
-        const double wb = c.scal()[S_wb], sub = c.scal()[S_gov_subsidy_level], price = c.scal()[S_price];
-        const double xi = c.par()[P_xi];
-        const double net = wb * (1.0 - c.par()[P_tax_rate]);
-        const double rp = 1.0 / price;
-        gk[G_net] = net; gk[G_sub] = sub;
-        gk[G_ir_emp] = C::kStrict ? net / price : net * rp; gk[G_ir_un] = C::kStrict ? sub / price : sub * rp;
-        gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = rp;
-    }
+    if (lane == 0) goods_constants(c);
     __syncwarp();
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int nch = (H + 31) / 32;
 
     // one chunk of households ahead: id, wealth, permanent income, employment link / dividend
@@ -941,37 +988,35 @@ __device__ void phase_goods_market(C &c)
         double pa = pa_n, pm = pm_n;
         const double dinc = dinc_n;
         if (ch + 1 < nch) fetch(ch + 1);
-        // a14 + a15: income, permanent income, consumption budget
-        double b = 0.0;
-        const double rpavg = gk[G_rpavg];
-        if (h >= 0) {
-            const double price = gk[G_price];
-            double ir;
-            if (h < W) { const bool emp = oc >= 0; pa = pa + (emp ? gk[G_net] : gk[G_sub]); ir = emp ? gk[G_ir_emp] : gk[G_ir_un]; }
-            else ir = C::kStrict ? dinc / price : dinc * rpavg;
-            pm = pm * gk[G_xi] + gk[G_omxi] * ir;
-            const double target = pm + (C::kStrict ? (gk[G_chi] * pa) / price : (gk[G_chi] * pa) * rpavg);
-            b = target * price;
-            if (b > pa) b = pa;
-            if (!(b > 0.0)) b = 0.0;
-            pa = pa - b;
-            c.perm(h) = pm;
+        double b;
+        GoodsList<C> cl;
+        goods_prepare<ZM>(c, mkt, z, h, oc, dinc, pa, pm, b, cl);
+        goods_commit_chunk<ZM>(c, mkt, acc, h, pa, b, cl);
+    }
+    // close: unpack the seller records.  The reductions above were issued by other lanes: fence, then
+    // read the accumulators where they live (L2)
+    __threadfence();
+    __syncwarp();
+    {
+        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
+        for (int f = lane; f < F; f += 32) {
+            const double2 r = mkt.yr[f];
+            const unsigned long long a = __ldcg(&acc[f]);
+            Yd[f] = C::kStrict ? r.y : (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
         }
-        // a16: candidates, sorted by price, packed
-        CandList<C::kStatic && DefaultLayout::kF <= 254> cl;
+    }
+    __syncwarp();
+}
+
+// commit (rounds) of one chunk of 32 prepared households; ends with what is left of b going back to PA
+template <int ZM, class C>
+__device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long long *acc, int h, double pa, double b, GoodsList<C> cl)
+{
+    const int lane = c.lane;
+    const unsigned lt = c.lt();
+    const double rpavg = c.gk()[G_rpavg];
+    {
         unsigned pend = __ballot_sync(FULL, b > 0.0);
-        if (b > 0.0) {
-            int cand[ZM]; unsigned key[ZM];
-            c.d.template candidates<ZM>(PH_GOODS, h, F, z, cand);
-            // key = price class (14 bits) | draw index (3 bits) | seller (14 bits): F <= 16383
-#pragma unroll
-            for (int k = 0; k < ZM; ++k)
-                key[k] = k < z ? (mkt.cls[cand[k]] << 17) | ((unsigned)k << 14) | (unsigned)cand[k] : 0xffffffffu;
-            sort_keys<ZM>(key);
-#pragma unroll
-            for (int k = 0; k < ZM; ++k)
-                if (k < z) cl.set(k, key[k] & 0x3fffu);
-        }
         // term: the seller this lane will buy from (>= 0), TERM_NONE (nothing left to visit / done)
         // or TERM_WALK (has budget and must walk down its list to the next seller with stock)
         enum { TERM_NONE = -1, TERM_WALK = -2 };
@@ -1086,19 +1131,6 @@ __device__ void phase_goods_market(C &c)
             }
         }
     }
-    // close: unpack the seller records.  The reductions above were issued by other lanes: fence, then
-    // read the accumulators where they live (L2)
-    __threadfence();
-    __syncwarp();
-    {
-        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
-        for (int f = lane; f < F; f += 32) {
-            const double2 r = mkt.yr[f];
-            const unsigned long long a = __ldcg(&acc[f]);
-            Yd[f] = C::kStrict ? r.y : (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
-        }
-    }
-    __syncwarp();
 }
 
 // a17 firms_accounting! (cats.py:397-398)

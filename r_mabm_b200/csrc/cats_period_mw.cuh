@@ -72,7 +72,6 @@ __device__ void mw_goods_market(C &c)
     // barriers per round)
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.mw + ML::bytes);
     OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord;
-    enum { G_net, G_sub, G_ir_emp, G_ir_un, G_xi, G_omxi, G_chi, G_price, G_rpavg };
     volatile double *gk = c.gk();
     unsigned *maskb = reinterpret_cast<unsigned *>(c.mw + ML::o_mask);
     // danger table: entries carry the stamp of the round that wrote them.  The stamp counts DOWN, so an atomic min
@@ -318,6 +317,113 @@ __device__ void mw_goods_market(C &c)
 #undef MWTICK
 }
 
+
+
+// ---------------------------------------------------------------------------------------------
+// The goods market as a PIPELINE (default-size economies): warp 0 commits, the other warps prepare.
+//
+// At F ~ 100 sellers a block-wide round costs 3-4 warp-wide ones (five barrier-separated stages against
+// shuffles), so the wide market of mw_goods_market only pays for large F.  Here the market keeps the one-warp
+// kernel's commit rounds (goods_commit_chunk: warp collectives, rule R2, ~67 rounds a period) and takes the
+// household preparation -- visiting order, record gather, income and budget, Philox candidates, price sort: 40 % of
+// the market's instructions, none of them dependent on the sellers' stock -- OFF the chain: producer warps fill a
+// ring of prepared chunks in shared memory, the consumer warp only commits.  Hand-over by mbarriers (full / empty per
+// slot, one arrival each): the pattern of a TMA pipeline with warps as the producers.
+// Every producer owns TWO slots and alternates between them, so it is never more than one barrier phase ahead of
+// the consumer (a one-bit phase parity cannot tell two phases apart).
+template <int S>
+struct PCSlots {   // lives in the MWLayout region (the wide market's tables are not used in this mode)
+    uint64_t full[S], empty[S];
+    int h[S][32];
+    double pa[S][32], b[S][32];
+    unsigned long long w0[S][32], w1[S][32];
+};
+static_assert(sizeof(PCSlots<2>) <= MWLayout<2>::bytes && sizeof(PCSlots<6>) <= MWLayout<4>::bytes &&
+              sizeof(PCSlots<14>) <= MWLayout<8>::bytes, "the ring must fit the multi-warp region");
+
+template <int ZM, class C>
+__device__ void mw_goods_market_pc(C &c)
+{
+    constexpr int NW = C::kWarps, P = NW - 1, S = 2 * P;
+    const auto &L = c.layout();
+    const int W = L.W, F = L.F, H = L.H, lane = c.lane, warp = c.warp;
+    const int z = c.z_c() < F ? c.z_c() : F;
+    Mkt mkt(c.sm + L.s_U, F);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(c.cf(C_Yd));   // GLOBAL, zeroed by produce
+    PCSlots<S> *ring = reinterpret_cast<PCSlots<S> *>(c.mw);
+    // chunk ch is producer (ch % P)'s k-th chunk, k = ch / P: slot (ch % P) + (k & 1) * P, barrier phase k >> 1
+    OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord;
+    if (warp == 0) {
+        ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
+        if (lane == 0) {
+            goods_constants(c);
+            for (int s = 0; s < S; ++s) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
+            fence_mbar_init();
+        }
+    } else ord.k = c.okeys();
+    __syncthreads();
+    const int nch = (H + 31) / 32;
+    if (warp == 0) {
+        // ---- consumer: chunk after chunk in visiting order
+        for (int ch = 0; ch < nch; ++ch) {
+            const int k = ch / P, s = ch % P + (k & 1) * P;
+            mbar_wait(&ring->full[s], (uint32_t)((k >> 1) & 1));
+            const int h = ring->h[s][lane];
+            const double pa = ring->pa[s][lane], b = ring->b[s][lane];
+            GoodsList<C> cl;
+            cl.w0 = (decltype(cl.w0))ring->w0[s][lane]; cl.w1 = (decltype(cl.w1))ring->w1[s][lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring->empty[s]);
+            goods_commit_chunk<ZM>(c, mkt, acc, h, pa, b, cl);
+        }
+    } else {
+        // ---- producers: warp p prepares chunks p, p + P, ... (each one chunk of loads ahead)
+        const int p = warp - 1;
+        int h_n = -1, oc_n = -1; double pa_n = 0.0, pm_n = 0.0, dinc_n = 0.0;
+        auto fetch = [&](int ch) {
+            const int pos = ch * 32 + lane;
+            h_n = -1; oc_n = -1; pa_n = 0.0; pm_n = 0.0; dinc_n = 0.0;
+            if (pos < H) {
+                const int h = ord.at(pos);
+                const double2 rec = c.hh()[h];
+                h_n = h; pa_n = rec.x; pm_n = rec.y;
+                if (h < W) oc_n = ((c.emp()[h >> 5] >> (h & 31)) & 1u) ? 0 : -1;
+                else if (h < W + F) dinc_n = c.cf(C_div_income)[h - W];
+                else dinc_n = c.kf(K_div_income)[h - W - F];
+            }
+        };
+        if (p < nch) fetch(p);
+        for (int ch = p; ch < nch; ch += P) {
+            const int h = h_n, oc = oc_n;
+            double pa = pa_n;
+            const double pm = pm_n, dinc = dinc_n;
+            if (ch + P < nch) fetch(ch + P);
+            double b;
+            GoodsList<C> cl;
+            goods_prepare<ZM>(c, mkt, z, h, oc, dinc, pa, pm, b, cl);
+            const int k = ch / P, s = p + (k & 1) * P;
+            mbar_wait(&ring->empty[s], (uint32_t)(((k >> 1) & 1) ^ 1));   // a fresh barrier counts as emptied once
+            ring->h[s][lane] = h; ring->pa[s][lane] = pa; ring->b[s][lane] = b;
+            ring->w0[s][lane] = (unsigned long long)cl.w0; ring->w1[s][lane] = (unsigned long long)cl.w1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring->full[s]);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // the ring's memory serves other phases until the next market: its barriers must not stay valid objects
+    if (c.tid < S) { mbar_inval(&ring->full[c.tid]); mbar_inval(&ring->empty[c.tid]); }
+    {
+        volatile double *gk = c.gk();
+        double *Yd = c.cf(C_Yd), *Q = c.cf(C_Q);
+        for (int f = c.tid; f < F; f += 32 * NW) {
+            const double2 r = mkt.yr[f];
+            const unsigned long long a = __ldcg(&acc[f]);
+            Yd[f] = (fx_to(a) * gk[G_price]) * r.y; Q[f] = c.cf(C_Y_prev)[f] - r.x;
+        }
+    }
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------------
 // The phases around the goods market, split over the warps of the block.
@@ -672,7 +778,8 @@ __device__ void mw_accounting(C &c)
 // default configuration with the layout resolved at compile time).  The matching chains of the labour and
 // capital-goods markets, the reward and the aggregate tracking are warp 0's (the one-warp code); everything else
 // is the block's.
-template <int ZM, int NW, int MINB, int MODE>
+// PIPE: the goods market as the producer / consumer pipeline (mw_goods_market_pc) instead of the block-wide one
+template <int ZM, int NW, int MINB, int MODE, bool PIPE>
 __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __grid_constant__ KArgs a)
 {
 #ifdef CATS_EMU
@@ -757,7 +864,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __g
             KTICK(5);
         }
         __syncthreads();
-        mw_goods_market<ZM>(c);
+        if constexpr (PIPE) mw_goods_market_pc<ZM>(c); else mw_goods_market<ZM>(c);
         KTICK(6);
         mw_accounting(c);
         KTICK(7);
@@ -835,7 +942,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __g
     }
 }
 
-KernelFn kernel_mw(int mode, int max_z, int nw);   // cats_inst_mw.cu
+KernelFn kernel_mw(int mode, int max_z, int nw, bool pipe);   // cats_inst_mw.cu
 int mw_extra_bytes(int nw, int F);
 
 }  // namespace cats

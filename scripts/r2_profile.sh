@@ -18,7 +18,7 @@ full c3 cats_period_kernel 1 period 16384 1 1000 100 20 1
 full c2mw cats_period_mw_kernel 1 period 1024 1 1000 100 20 0
 full c5mw cats_period_mw_kernel 1 period 256 1 10000 1000 200 0
 full c5one cats_period_kernel 1 period 256 1 10000 1000 200 1
-full tape cats_period_kernel 1 tape 1024
+full tape cats_period_kernel 0 tape 1024
 full q cats_q_kernel 5 rollout 4096 10
 full init cats_init_kernel 0 period 16384 1 1000 100 20 1
 ls -la $O/*.ncu-rep

@@ -17,9 +17,11 @@ void run(const KArgs &a)
 }
 
 template <int ZM, int NW, int MODE>
-void run_mw(const KArgs &a)
+void run_mw(const KArgs &a, bool pipe)
 {
-    simt::launch((unsigned)a.B, 32u * NW, (size_t)a.slice + MWLayout<NW>::total(a.L.F), [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE>(a); });
+    const size_t smem = (size_t)a.slice + MWLayout<NW>::total(a.L.F);
+    if (pipe) simt::launch((unsigned)a.B, 32u * NW, smem, [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE, true>(a); });
+    else simt::launch((unsigned)a.B, 32u * NW, smem, [&]() { cats_period_mw_kernel<ZM, NW, 1, MODE, false>(a); });
 }
 
 }  // namespace
@@ -27,16 +29,16 @@ void run_mw(const KArgs &a)
 extern "C" {
 
 // the multi-warp kernel: nw warps per economy; mode 1 (any size) or 2 (default configuration)
-int emu_step_mw(const cats_step_args *s, int mode, int nw)
+int emu_step_mw(const cats_step_args *s, int mode, int nw, int pipe)
 {
     KArgs a;
     fill_kargs(s, a);
     if (s->d_tape || s->stop_phase || s->d_debug || s->d_active || (s->flags & CATS_FLAG_STRICT)) return -1;
     if (mode == 2) {
         if (s->W != DefaultLayout::kW || s->F != DefaultLayout::kF || s->N != DefaultLayout::kN) return -1;
-        if (nw == 2) run_mw<5, 2, 2>(a); else if (nw == 4) run_mw<5, 4, 2>(a); else run_mw<5, 8, 2>(a);
+        if (nw == 2) run_mw<5, 2, 2>(a, pipe); else if (nw == 4) run_mw<5, 4, 2>(a, pipe); else run_mw<5, 8, 2>(a, pipe);
     } else {
-        if (nw == 2) run_mw<MAX_Z, 2, 1>(a); else if (nw == 4) run_mw<MAX_Z, 4, 1>(a); else run_mw<MAX_Z, 8, 1>(a);
+        if (nw == 2) run_mw<MAX_Z, 2, 1>(a, pipe); else if (nw == 4) run_mw<MAX_Z, 4, 1>(a, pipe); else run_mw<MAX_Z, 8, 1>(a, pipe);
     }
     return 0;
 }

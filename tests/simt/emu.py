@@ -49,7 +49,7 @@ def lib() -> C.CDLL:
         L.emu_init.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         L.emu_step.argtypes = [C.POINTER(nat.StepArgs), C.c_int, C.c_int]
         L.emu_set_schedule.argtypes = [C.c_int]
-        L.emu_step_mw.argtypes = [C.POINTER(nat.StepArgs), C.c_int, C.c_int]
+        L.emu_step_mw.argtypes = [C.POINTER(nat.StepArgs), C.c_int, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -60,8 +60,9 @@ class EmuCats:
     1 in reverse, >= 2 a pseudo-random order per scheduling round."""
 
     def __init__(self, B, W=1000, F=100, N=20, params=None, n_agents=0, seed=0, economy_base=0, mode=1, g=1,
-                 schedule=0, strict=False, flags=0, bankruptcy_reward=-100.0, warps=1):
+                 schedule=0, strict=False, flags=0, bankruptcy_reward=-100.0, warps=1, pipe=False):
         self.warps = warps      # > 1: the multi-warp kernel (one block per economy)
+        self.pipe = pipe        # its goods market as the producer / consumer pipeline instead of the block-wide one
         self.B, self.W, self.F, self.N = B, W, F, N
         self.n_agents, self.seed, self.economy_base = n_agents, seed, economy_base
         self.mode, self.g, self.schedule, self.strict = mode, g, schedule, strict
@@ -147,7 +148,7 @@ class EmuCats:
         mode = 0 if (tape is not None or stop_phase or debug is not None) else self.mode
         lib().emu_set_schedule(self.schedule)
         if self.warps > 1 and mode != 0:
-            rc = lib().emu_step_mw(C.byref(a), mode, self.warps)
+            rc = lib().emu_step_mw(C.byref(a), mode, self.warps, int(self.pipe))
         else:
             rc = lib().emu_step(C.byref(a), mode, self.g)
         assert rc == 0, "emulated kernel: unsupported combination"

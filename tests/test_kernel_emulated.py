@@ -152,3 +152,19 @@ def test_multiwarp_rl_step():
             r_obs, r_rew = o.step(actions=acts[b], flags=0)
             assert np.array_equal(bits(obs[b]), bits(r_obs)) and np.array_equal(bits(rew[b]), bits(r_rew))
         assert compare_state(env, orcs, f"t={t}") == []
+
+
+@pytest.mark.parametrize("W,F,N,warps,mode,schedule", [(1000, 100, 20, 2, 2, 0), (1000, 100, 20, 4, 2, 3), (1000, 100, 20, 8, 1, 1),
+                                                         (300, 30, 8, 4, 1, 5), (130, 7, 2, 8, 1, 6), (37, 3, 1, 2, 1, 1)])
+def test_multiwarp_pipelined_goods_market(W, F, N, warps, mode, schedule):
+    """mw_goods_market_pc: one warp commits with the one-warp kernel's rounds, the others prepare households into a
+    ring of shared-memory slots (mbarrier hand-over, two slots per producer)."""
+    B, T = 2, 60
+    env = EmuCats(B, W=W, F=F, N=N, seed=29, mode=mode, warps=warps, schedule=schedule, pipe=True)
+    orcs = make_oracles(B, W, F, N, seed=29)
+    for t0 in range(0, T, 20):
+        stats = env.run(20, want_stats=True)
+        ref = orc.run_batch(orcs, 20, n_threads=B)
+        bad = compare_state(env, orcs, f"pipeline, {warps} warps t={t0 + 20}")
+        assert bad == [], "\n".join(bad)
+        assert np.array_equal(stats.view(np.uint64), ref.view(np.uint64))

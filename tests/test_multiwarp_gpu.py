@@ -17,6 +17,7 @@ def lib():
     L = nat.load()
     yield L
     L.cats_debug_set_warps(0)
+    L.cats_debug_set_pipe(-1)
 
 
 def _env(B, **kw):
@@ -24,9 +25,10 @@ def _env(B, **kw):
     return BatchedCats(B, **kw)
 
 
-@pytest.mark.parametrize("warps", [2, 4, 8])
-def test_default_size_120_periods(lib, warps):
-    lib.cats_debug_set_warps(warps)
+@pytest.mark.parametrize("warps,pipe", [(2, 0), (4, 0), (8, 0), (2, 1), (4, 1), (8, 1)])
+def test_default_size_120_periods(lib, warps, pipe):
+    """pipe 0: the block-wide goods market; 1: the producer / consumer pipeline."""
+    lib.cats_debug_set_warps(warps); lib.cats_debug_set_pipe(pipe)
     B = 8
     env = _env(B, seed=2024)
     orcs = make_oracles(B, 1000, 100, 20, seed=2024)
@@ -54,8 +56,9 @@ def test_ragged_sizes(lib, W, F, N, zs, warps):
         assert bad == [], "\n".join(bad)
 
 
-def test_scaled_economy_10x_eight_warps(lib):
-    lib.cats_debug_set_warps(8)
+@pytest.mark.parametrize("pipe", [0, 1])
+def test_scaled_economy_10x_eight_warps(lib, pipe):
+    lib.cats_debug_set_warps(8); lib.cats_debug_set_pipe(pipe)
     B, W, F, N = 3, 10000, 1000, 200
     env = _env(B, W=W, F=F, N=N, seed=51)
     orcs = make_oracles(B, W, F, N, seed=51)
@@ -75,8 +78,8 @@ def test_every_shape_gives_the_same_bits_with_actions_and_heterogeneous_paramete
         p.update(chi=0.04 + 0.001 * i, Iprob=0.2 + 0.005 * i)
     ref = None
     acts = torch.full((B, A, 2), 1.03, dtype=torch.float64, device="cuda")
-    for warps in (1, 2, 4, 8, 0):
-        lib.cats_debug_set_warps(warps)
+    for warps, pipe in ((1, -1), (2, 0), (4, 0), (8, 0), (2, 1), (4, 1), (8, 1), (0, -1)):
+        lib.cats_debug_set_warps(warps); lib.cats_debug_set_pipe(pipe)
         env = _env(B, W=400, F=40, N=8, params=[dict(p) for p in plist], n_agents=A, seed=77)
         env.run(25)
         obs, rew, term, st = env.step(acts, want_stats=True)
@@ -87,7 +90,7 @@ def test_every_shape_gives_the_same_bits_with_actions_and_heterogeneous_paramete
             ref = got
         else:
             for a, b in zip(got, ref):
-                assert torch.equal(a, b), f"{warps} warps"
+                assert torch.equal(a, b), f"{warps} warps, pipe {pipe}"
 
 
 def test_config2_width_auto_shape_matches_one_warp_kernel(lib):

@@ -488,15 +488,48 @@ __device__ void phase_job_search(C &c)
                 U += __popc(bal);
             }
         }
-        if (U <= JOB_SORT_MAX && U <= cap3) {
+        // Rank by position.  With room for a W-bit bitmap of the positions and its word prefix (the firing / capital
+        // scratch, idle here) a seeker's rank is the number of bits below its own: O(U + W / 32), any U that fits the
+        // list; otherwise all pairs, up to JOB_SORT_MAX seekers.
+        const int nwords = (W + 31) >> 5;
+        const bool bitmap_fits = 2 * nwords <= L.F + L.N;
+        if (U <= cap3 && (bitmap_fits || U <= JOB_SORT_MAX)) {
             __syncwarp();
-            for (int i = lane; i < U; i += 32) posv[i] = (unsigned short)ord.position_of((int)byidx[i]);
-            __syncwarp();
-            for (int i = lane; i < U; i += 32) {
-                const unsigned mine = posv[i];
-                int r = 0;
-                for (int j = 0; j < U; ++j) r += posv[j] < mine ? 1 : 0;   // positions are distinct
-                seekers[r] = byidx[i];
+            if (bitmap_fits) {
+                unsigned *bitmap = reinterpret_cast<unsigned *>(c.iat(L.s_ic));
+                int *prefix = c.iat(L.s_ic) + nwords;
+                for (int i = lane; i < nwords; i += 32) bitmap[i] = 0u;
+                __syncwarp();
+                for (int i = lane; i < U; i += 32) {
+                    const int pos = ord.position_of((int)byidx[i]);
+                    posv[i] = (unsigned short)pos;
+                    atomicOr(&bitmap[pos >> 5], 1u << (pos & 31));
+                }
+                __syncwarp();
+                int run = 0;
+                for (int base = 0; base < nwords; base += 32) {
+                    const int i = base + lane;
+                    const int n = i < nwords ? __popc(bitmap[i]) : 0;
+                    int incl = n;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
+                    if (i < nwords) prefix[i] = run + incl - n;
+                    run += __shfl_sync(FULL, incl, 31);
+                }
+                __syncwarp();
+                for (int i = lane; i < U; i += 32) {
+                    const int pos = (int)posv[i];
+                    seekers[prefix[pos >> 5] + __popc(bitmap[pos >> 5] & ((1u << (pos & 31)) - 1u))] = byidx[i];
+                }
+            } else {
+                for (int i = lane; i < U; i += 32) posv[i] = (unsigned short)ord.position_of((int)byidx[i]);
+                __syncwarp();
+                for (int i = lane; i < U; i += 32) {
+                    const unsigned mine = posv[i];
+                    int r = 0;
+                    for (int j = 0; j < U; ++j) r += posv[j] < mine ? 1 : 0;   // positions are distinct
+                    seekers[r] = byidx[i];
+                }
             }
             total = U;
             listed = true;
@@ -1081,14 +1114,22 @@ __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long
             const unsigned movers = __ballot_sync(FULL, has && (sold || !full));
             bool endangered = false;
             if (movers) {
-                unsigned todo = movers, unc = movers;
-                while (todo) {
+                // only lanes that could still commit a purchase matter (`open`), and only uncertain lanes BELOW the
+                // highest of them can endanger one: most lanes queued behind a sell-out drop out of the loop
+                const unsigned fullm = __ballot_sync(FULL, full);
+                unsigned open = __ballot_sync(FULL, has && !sold);
+                unsigned unc = movers, todo = movers;
+                while (open) {
+                    todo &= (1u << (31 - __clz((int)open))) - 1u;   // below the highest open lane
+                    if (!todo) break;
                     const int i = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const auto li = cl.from_lane(i);
-                    const bool hit = has && !sold && lane > i && li.contains(term);
+                    const bool hit = has && !sold && !endangered && lane > i && li.contains(term);
                     endangered |= hit;
-                    const unsigned newly = __ballot_sync(FULL, hit && full) & ~unc;
+                    const unsigned hitm = __ballot_sync(FULL, hit);
+                    open &= ~hitm;
+                    const unsigned newly = hitm & fullm & ~unc;
                     unc |= newly; todo |= newly;
                 }
             }

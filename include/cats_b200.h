@@ -52,6 +52,7 @@ extern "C" {
 /* per-economy status bits (replace the reference's warnings.warn, cats.py:518,535) */
 #define CATS_STATUS_DEPVAL_DIV0 1u
 #define CATS_STATUS_PROFIT_NAN 2u
+#define CATS_STATUS_TAPE_RANGE 8u    /* replay: the tape held a candidate or a visiting-order entry outside its range (taken as 0): results invalid */
 #define CATS_STATUS_Z_MISMATCH 4u   /* cats_step_args.z_all was set but this economy's parameters disagree: its results are invalid */
 
 /* columns of the per-period statistics row (the aggregates Cats._get_info reads, cats.py:567-607) */

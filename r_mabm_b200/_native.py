@@ -20,7 +20,7 @@ N_STATS = 16
 MAX_Z = 8
 
 FLAG_BURNIN, FLAG_LOG, FLAG_AVG_PRICE, FLAG_REWARD_RMS, FLAG_STRICT = 1, 2, 4, 8, 16
-STATUS_DEPVAL_DIV0, STATUS_PROFIT_NAN, STATUS_Z_MISMATCH = 1, 2, 4
+STATUS_DEPVAL_DIV0, STATUS_PROFIT_NAN, STATUS_Z_MISMATCH, STATUS_TAPE_RANGE = 1, 2, 4, 8
 OK, EINVAL, ECUDA, ESMEM = 0, -1, -2, -3
 
 STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_tot", "gdp_deflator",

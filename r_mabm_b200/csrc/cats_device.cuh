@@ -148,6 +148,7 @@ struct DrawsT {
     uint32_t epi;               // episode << 12: rides in counter word 1 above the phase and block bits
     const TapeOff *tp;          // tape record layout (kernel parameter space: costs no registers)
     const int *tape_z;          // z_c, z_k, z_e the tape was laid out with
+    int *bad;                   // tape mode: status word that takes CATS_STATUS_TAPE_RANGE when a taped index is out of range
 
     __device__ __forceinline__ uint4 philox(uint32_t agent, uint32_t phase, uint32_t block) const
     {
@@ -177,8 +178,15 @@ struct DrawsT {
             else if (phase == PH_CAP) { off = tp->cap_cand; zz = tape_z[1]; }
             else { off = tp->goods_cand; zz = tape_z[0]; }
             const int *src = reinterpret_cast<const int *>(tape + off) + (size_t)agent * (size_t)zz;
+            // a foreign tape is untrusted input: an index outside [0, n) would be a wild shared-memory access
+            bool oob = false;
 #pragma unroll
-            for (int k = 0; k < ZM; ++k) out[k] = k < z ? src[k] : 0;
+            for (int k = 0; k < ZM; ++k) {
+                int v = k < z ? src[k] : 0;
+                if ((unsigned)v >= (unsigned)n) { v = 0; oob = true; }
+                out[k] = v;
+            }
+            if (oob) atomicOr(bad, 8);   // CATS_STATUS_TAPE_RANGE
             return;
         }
         // ONE Philox block: draw k < 4 uses word k, draw k >= 4 re-uses the low half of that product
@@ -234,6 +242,7 @@ __device__ __forceinline__ uint32_t perm_hash(uint32_t v, uint32_t k)
 template <uint32_t NS, bool TAPE>
 struct OrderT {
     volatile OrderKeys *k;
+    int *bad;   // tape mode: the status word (see DrawsT::bad)
     struct Dims { uint32_t a, b, m, n; };
     __device__ __forceinline__ Dims dims() const
     {
@@ -248,6 +257,7 @@ struct OrderT {
     __device__ __forceinline__ void init(const D &d, int market, const OrderDims &dims, OrderKeys *keys, int lane)
     {
         k = keys;
+        bad = d.bad;
         if (lane == 0) {
             keys->a = dims.a; keys->b = dims.b; keys->m = dims.m; keys->n = dims.n;
             keys->tape_order = nullptr;
@@ -265,7 +275,11 @@ struct OrderT {
     {
         if (TAPE) {
             const int *to = k->tape_order;
-            if (to) return to[pos];
+            if (to) {
+                int v = to[pos];
+                if ((unsigned)v >= k->n) { v = 0; atomicOr(bad, 8); }   // untrusted input: CATS_STATUS_TAPE_RANGE
+                return v;
+            }
         }
         const Dims dm = dims();
         const uint32_t a = dm.a, b = dm.b, m = dm.m, n = dm.n;

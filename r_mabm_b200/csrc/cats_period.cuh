@@ -1703,6 +1703,7 @@ __global__ void __launch_bounds__(32 * G, MINB) cats_period_kernel(const __grid_
     c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
     c.d.tp = &a.T;
     c.d.tape_z = a.tape_z;
+    c.d.bad = &c.misc()[M_STATUS];
 
     unsigned launch_status = 0u;   // lane 0: the status bits raised by THIS launch (what d_status reports)
     for (int t = 0; t < a.n_periods; ++t) {

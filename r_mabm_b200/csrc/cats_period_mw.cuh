@@ -90,7 +90,7 @@ __device__ void mw_goods_market(C &c)
             gk[G_net] = net; gk[G_sub] = sub; gk[G_ir_emp] = net * rp; gk[G_ir_un] = sub * rp;
             gk[G_xi] = xi; gk[G_omxi] = 1.0 - xi; gk[G_chi] = c.par()[P_chi]; gk[G_price] = price; gk[G_rpavg] = rp;
         }
-    } else ord.k = c.okeys();
+    } else { ord.k = c.okeys(); ord.bad = c.d.bad; }
     for (int i = tid; i < 2 * MW_ROWS * NW; i += T) maskb[i] = 0u;
     for (int i = tid; i < MW_ROWS; i += T) dangb[i] = 0x7fffffff;
     for (int f = tid; f < F; f += T) acc[f] = 0ull;
@@ -824,6 +824,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) cats_period_mw_kernel(const __g
     c.d.economy = (uint32_t)(a.economy_base + (unsigned long long)b);
     c.d.tp = &a.T;
     c.d.tape_z = a.tape_z;
+    c.d.bad = &c.misc()[M_STATUS];
     unsigned launch_status = 0u;
 #ifdef CATS_PROFILE_PHASES
     long long tk = 0;

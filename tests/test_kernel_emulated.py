@@ -168,3 +168,21 @@ def test_multiwarp_pipelined_goods_market(W, F, N, warps, mode, schedule):
         bad = compare_state(env, orcs, f"pipeline, {warps} warps t={t0 + 20}")
         assert bad == [], "\n".join(bad)
         assert np.array_equal(stats.view(np.uint64), ref.view(np.uint64))
+
+
+def test_out_of_range_tape_entries_are_flagged_not_followed():
+    """A foreign tape is untrusted input: an index outside its range is taken as 0 and raises CATS_STATUS_TAPE_RANGE."""
+    from r_mabm_b200 import _native as nat
+    W, F, N = 200, 20, 5
+    env = EmuCats(2, W=W, F=F, N=N, seed=5, mode=0)
+    rng = np.random.default_rng(3)
+    env.run(3, tape=foreign_tapes(rng, 6, W, F, N, 5, 2, 5).reshape(2, 3, -1))
+    assert not (env.status & nat.STATUS_TAPE_RANGE).any()
+    off = orc.tape_offsets(W, F, N, 5, 2, 5)
+    recs = foreign_tapes(rng, 2, W, F, N, 5, 2, 5).reshape(2, 1, -1)
+    gc = recs[0, 0, off["goods_cand"]: off["goods_cand"] + 4 * 5 * (W + F + N)].view(np.int32).reshape(-1, 5)
+    gc[:, 0] = 10 ** 6                                    # (a household without a budget draws no candidates: hit them all)
+    recs[1, 0, off["job_order"] + 8: off["job_order"] + 12] = np.array([-7], dtype=np.int32).view(np.uint8)
+    env.run(1, tape=recs)
+    assert (env.status & nat.STATUS_TAPE_RANGE).all()
+    assert np.isfinite(env.field("scal").numpy()).all()

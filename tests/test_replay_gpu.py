@@ -170,3 +170,26 @@ def test_active_mask_with_tape_or_debug_stop_is_rejected():
     a.d_active = act.data_ptr(); a.d_tape = tape.data_ptr()
     a.tape_z[0], a.tape_z[1], a.tape_z[2] = 5, 2, 5
     assert env._lib.cats_step(C.byref(a)) == nat.EINVAL
+
+
+def test_out_of_range_tape_entries_are_flagged_not_followed():
+    """A foreign tape is untrusted input: an index outside its range is taken as 0 and raises CATS_STATUS_TAPE_RANGE
+    (a wild shared-memory access otherwise)."""
+    from r_mabm_b200 import _native as nat
+    W, F, N = 1000, 100, 20
+    env = _env(2, seed=5)
+    env.run(20)
+    rng = np.random.default_rng(3)
+    off = orc.tape_offsets(W, F, N, 5, 2, 5)
+    recs = foreign_tapes(rng, 2, W, F, N, 5, 2, 5).reshape(2, 1, -1)
+    env.run(1, tape=torch.from_numpy(recs).cuda().view(-1))
+    torch.cuda.synchronize()
+    assert int(env._status.max()) == 0
+    recs = foreign_tapes(rng, 2, W, F, N, 5, 2, 5).reshape(2, 1, -1)
+    gc = recs[0, 0, off["goods_cand"]: off["goods_cand"] + 4 * 5 * (W + F + N)].view(np.int32).reshape(-1, 5)
+    gc[:, 0] = 10 ** 6                                    # (a household without a budget draws no candidates: hit them all)
+    recs[1, 0, off["job_order"] + 8: off["job_order"] + 12] = np.array([-7], dtype=np.int32).view(np.uint8)
+    env.run(1, tape=torch.from_numpy(recs).cuda().view(-1))
+    torch.cuda.synchronize()
+    assert (env._status.cpu().numpy() & nat.STATUS_TAPE_RANGE).all()
+    assert torch.isfinite(env.field("scal")).all()

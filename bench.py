@@ -446,7 +446,7 @@ def run_b200(args):
                          "issue_slots": issue,
                          "note": "bound by dependent-instruction latency and issue slots of the serial matching "
                                  "markets, not by bandwidth; see DESIGN.md 2.3"},
-            "clocks": clocks, "launch": env.launch_info(), "mean_unemployment_check": un_mean,
+            "clocks": clocks, "launch": env.launch_shape(), "mean_unemployment_check": un_mean,
         }
         if also is not None:
             line["also_measured"] = also

@@ -207,6 +207,12 @@ int cats_workset_field_info(int W, int F, int N, const char *name, uint64_t *byt
 int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
                      int32_t *economies_per_sm, int32_t *num_sms);
 
+/* The kernel shape cats_step picks for a production launch of B economies of this size on the current device: warps
+ * per economy (1 = the one-warp-per-economy kernel, 4 / 8 = one thread block per economy), economies per block (one-warp
+ * kernel), and whether the multi-warp kernel runs its goods market as the producer / consumer pipeline. */
+int cats_launch_shape(int W, int F, int N, int64_t B, int32_t *warps_per_economy, int32_t *economies_per_block,
+                      int32_t *pipelined_goods_market);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t cats_launch_count(void);
 

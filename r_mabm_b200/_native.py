@@ -34,7 +34,7 @@ EXPORTS = [
     "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_reset_masked", "cats_step", "cats_q_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_host_block_offsets", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
     "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group", "cats_debug_set_static",
-    "cats_debug_set_warps", "cats_debug_set_pipe",
+    "cats_debug_set_warps", "cats_debug_set_pipe", "cats_launch_shape",
 ]
 
 
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     L.cats_step_host.argtypes = [C.POINTER(StepArgs), C.c_void_p]
     L.cats_host_block_offsets.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.cats_launch_info.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int32)] * 4
+    L.cats_launch_shape.argtypes = [C.c_int] * 3 + [C.c_int64] + [C.POINTER(C.c_int32)] * 3
     L.cats_launch_count.restype = C.c_uint64
     L.cats_debug_phase_cycles.argtypes = [C.c_void_p]
     L.cats_debug_phase_cycles.restype = None

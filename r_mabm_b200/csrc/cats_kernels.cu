@@ -323,6 +323,20 @@ int cats_launch_info(int W, int F, int N, int32_t *threads, int32_t *smem_bytes,
     return CATS_OK;
 }
 
+int cats_launch_shape(int W, int F, int N, int64_t B, int32_t *warps_per_economy, int32_t *economies_per_block,
+                      int32_t *pipelined_goods_market)
+{
+    if (int rc = check_sizes(W, F, N)) return rc;
+    Layout L = make_layout(W, F, N);
+    int dev = 0; DevInfo di;
+    if (int rc = device_info(&dev, &di)) return rc;
+    const int nw = choose_warps(L, B, di.sms);
+    if (warps_per_economy) *warps_per_economy = nw;
+    if (economies_per_block) *economies_per_block = nw > 1 ? 1 : choose_group(L, B, di.sms);
+    if (pipelined_goods_market) *pipelined_goods_market = nw > 1 && choose_pipe(L, nw) ? 1 : 0;
+    return CATS_OK;
+}
+
 int cats_init(void *d_blobs, int64_t B, int W, int F, int N, const double *d_params, int64_t params_stride,
               void *stream)
 {

@@ -498,11 +498,17 @@ __device__ void mw_fire(C &c)
         const int f1 = scr[0], total = scr[1];
         if (f1 == f0) { f0 = f0 + 1; __syncthreads(); continue; }
         if (total > 0) {
-            for (int w = tid; w < W; w += T) {
-                const int f = c.Oc()[w];
-                if (f >= f0 && f < f1 && c.vac()[f] < 0) {
-                    const int slot = atomicAdd(&ic[f], 0x10000) >> 16;
-                    pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
+            for (int w0 = tid; w0 < W; w0 += 4 * T) {
+                int ff[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int w = w0 + u * T; ff[u] = w < W ? c.Oc()[w] : -1; }   // 4 loads in flight
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = ff[u], w = w0 + u * T;
+                    if (f >= f0 && f < f1 && c.vac()[f] < 0) {
+                        const int slot = atomicAdd(&ic[f], 0x10000) >> 16;
+                        pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
+                    }
                 }
             }
             __syncthreads();
@@ -544,18 +550,25 @@ __device__ void mw_job_search(C &c)
     if (tid == 0) cnt[0] = 0;
     __syncthreads();
     const int nwords = (W + 31) >> 5;
-    for (int word = c.warp; word < nwords; word += NW) {
-        const int w = word * 32 + lane;
-        const bool un = w < W && c.Oc()[w] < 0;
-        const unsigned bal = __ballot_sync(FULL, un);
-        int base = 0;
-        if (lane == 0) {
-            c.emp()[word] = ~bal;   // employed bits for the goods market (hires are added by the matching rounds)
-            if (bal) base = atomicAdd(&cnt[0], __popc(bal));
+    for (int word0 = c.warp; word0 < nwords; word0 += 4 * NW) {
+        int oc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int w = (word0 + u * NW) * 32 + lane; oc[u] = w < W ? c.Oc()[w] : 0; }   // 4 loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int word = word0 + u * NW, w = word * 32 + lane;
+            if (word >= nwords) break;
+            const bool un = w < W && oc[u] < 0;
+            const unsigned bal = __ballot_sync(FULL, un);
+            int base = 0;
+            if (lane == 0) {
+                c.emp()[word] = ~bal;   // employed bits for the goods market (hires are added by the matching rounds)
+                if (bal) base = atomicAdd(&cnt[0], __popc(bal));
+            }
+            base = __shfl_sync(FULL, base, 0);
+            const int at = base + __popc(bal & c.lt());
+            if (un && at < cap3) byidx[at] = (unsigned short)w;
         }
-        base = __shfl_sync(FULL, base, 0);
-        const int at = base + __popc(bal & c.lt());
-        if (un && at < cap3) byidx[at] = (unsigned short)w;
     }
     __syncthreads();
     const int U = cnt[0];
@@ -612,12 +625,49 @@ __device__ void mw_produce(C &c)
     produce_k_loop(c, lo, hi);
     __syncthreads();
     Mkt mkt(c.sm + L.s_U, F);
-    for (int f = c.tid; f < F; f += T) {
-        const double pf = mkt.p[f];
-        unsigned n = 0u;
+    // price class = number of strictly cheaper sellers.  Few sellers: count (F * F / T compares per thread).  Many
+    // (the 10x economy: 1,000): sort the prices in the goods market's tables (idle until then) with a bitonic
+    // network -- a positive double orders like its bit pattern -- and a seller's class is the first position of its
+    // price in the sorted row.
+    int n2 = 1;
+    while (n2 < F) n2 <<= 1;
+    if (F <= 256 || n2 * 10 > MWLayout<C::kWarps>::bytes) {
+        for (int f = c.tid; f < F; f += T) {
+            const double pf = mkt.p[f];
+            unsigned n = 0u;
 #pragma unroll 4
-        for (int g = 0; g < F; ++g) n += mkt.p[g] < pf ? 1u : 0u;
-        mkt.cls[f] = n;
+            for (int g = 0; g < F; ++g) n += mkt.p[g] < pf ? 1u : 0u;
+            mkt.cls[f] = n;
+        }
+        return;
+    }
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(c.mw);
+    unsigned short *idx = reinterpret_cast<unsigned short *>(c.mw + 8 * (size_t)n2);
+    for (int i = c.tid; i < n2; i += T) {
+        key[i] = i < F ? (unsigned long long)__double_as_longlong(mkt.p[i]) : ~0ull;
+        idx[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = c.tid; t < (n2 >> 1); t += T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // the lower index of the t-th pair at distance j
+                const int p = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long a = key[i], b = key[p];
+                if ((a > b) == up) {
+                    key[i] = b; key[p] = a;
+                    const unsigned short ia = idx[i]; idx[i] = idx[p]; idx[p] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = c.tid; r < F; r += T) {
+        int first = r;
+        const unsigned long long kr = key[r];
+        while (first > 0 && key[first - 1] == kr) --first;   // equal prices share the class (ties are rare)
+        mkt.cls[idx[r]] = (unsigned)first;
     }
 }
 

@@ -370,6 +370,14 @@ class BatchedCats:
         return {"threads_per_block": t.value, "economies_per_block": t.value // 32, "smem_bytes_per_block": s.value,
                 "economies_per_sm": b.value, "num_sms": n.value}
 
+    def launch_shape(self) -> dict:
+        """The kernel shape the library picks for THIS batch (see cats_launch_shape)."""
+        w, g, p = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.cats_launch_shape(self.W, self.F, self.N, self.B, C.byref(w), C.byref(g), C.byref(p)))
+        return {"warps_per_economy": w.value, "economies_per_block": g.value,
+                "goods_market": ("pipelined" if p.value else "block-wide") if w.value > 1 else "warp-wide"}
+
     def algo_bytes_per_period(self) -> int:
         """CATS_ALGO_BYTES (docs/DESIGN.md): every state byte read once and written once."""
         return 2 * self.blob_bytes

@@ -4,6 +4,7 @@ rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 nep = float(sys.argv[5]) if len(sys.argv) > 5 else 0
 import tempfile, os
+_hits = set()
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
 cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
@@ -13,6 +14,8 @@ cur = None; infn = False
 for ln in dis:
     if ln.startswith(".text."):
         infn = kern in ln
+        if infn: _hits.add(ln.strip())
+        assert len(_hits) <= 1, f"kernel substring is ambiguous (give the full mangled argument list): {sorted(_hits)}"
         continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)

@@ -9,7 +9,11 @@ cubin=[f for f in os.listdir(d) if f.endswith('.cubin')][0]
 dis=subprocess.run(['nvdisasm','-g',os.path.join(d,cubin)],capture_output=True,text=True).stdout.splitlines()
 off2line={};cur=None;infn=False
 for ln in dis:
-    if ln.startswith('.text.'): infn=kern in ln; continue
+    if ln.startswith(".text."):
+        infn = kern in ln
+        if infn: _hits.add(ln.strip())
+        assert len(_hits) <= 1, f"kernel substring is ambiguous (give the full mangled argument list): {sorted(_hits)}"
+        continue
     if not infn: continue
     m=re.search(r'//## File "([^"]+)", line (\d+)',ln)
     if m: cur=(os.path.basename(m.group(1)),int(m.group(2))); continue

@@ -2,13 +2,18 @@
 import csv, re, subprocess, sys, collections, os, tempfile
 rep, so, kern, nep = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3], float(sys.argv[4])
 thr = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
+_hits = set()
 d = tempfile.mkdtemp()
 subprocess.run(f"cd {d} && cuobjdump -xelf all {so} > /dev/null", shell=True, check=True)
 cubins = sorted(f for f in os.listdir(d) if f.endswith(".cubin"))   # one per translation unit
 dis = [l for cb in cubins for l in subprocess.run(["nvdisasm", "-g", os.path.join(d, cb)], capture_output=True, text=True).stdout.splitlines()]
 off2line = {}; cur = None; infn = False
 for ln in dis:
-    if ln.startswith(".text."): infn = kern in ln; continue
+    if ln.startswith(".text."):
+        infn = kern in ln
+        if infn: _hits.add(ln.strip())
+        assert len(_hits) <= 1, f"kernel substring is ambiguous (give the full mangled argument list): {sorted(_hits)}"
+        continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue

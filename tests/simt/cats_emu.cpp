@@ -46,6 +46,9 @@ int emu_step_mw(const cats_step_args *s, int mode, int nw, int pipe)
 
 void emu_set_schedule(int s) { simt::g_schedule = s; }
 
+// development counters (builds with -DCATS_EMU_COUNT): copies them out and clears them
+void emu_counts(long long *out) { for (int i = 0; i < 8; ++i) { out[i] = simt::g_count[i]; simt::g_count[i] = 0; } }
+
 int emu_init(unsigned char *blobs, long long B, int W, int F, int N, const double *params, long long params_stride,
              const unsigned char *active)
 {

@@ -6,6 +6,7 @@ namespace simt {
 Block *g_blk = nullptr;
 Fiber *g_cur = nullptr;
 int g_schedule = 0;
+long long g_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 unsigned long long g_clock = 0;
 
 // x86-64 SysV context switch: callee-saved registers on the old stack, swap stack pointers

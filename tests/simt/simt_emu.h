@@ -66,6 +66,7 @@ struct Block {
 extern Block *g_blk;
 extern Fiber *g_cur;
 extern int g_schedule;   // 0 forward, 1 reverse, >= 2 pseudo-random (seed)
+extern long long g_count[8];   // development counters (kernel code under CATS_EMU_COUNT bumps them; emu_counts reads them)
 extern unsigned long long g_clock;
 
 extern "C" void simt_switch(void **save_sp, void *load_sp);

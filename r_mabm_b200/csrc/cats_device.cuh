@@ -482,7 +482,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
             "selp.u32 %0, 1, 0, P1;\n"
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(256);
+#ifndef CATS_PRODUCER_SLEEP_NS
+#define CATS_PRODUCER_SLEEP_NS 256
+#endif
+        __nanosleep(CATS_PRODUCER_SLEEP_NS);
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)

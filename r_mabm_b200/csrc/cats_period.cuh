@@ -423,9 +423,13 @@ __device__ void phase_fire(C &c, int limit)
                 fnext = w + 32 < W ? c.Oc()[w + 32] : -1;   // next load in flight while this worker is handled
                 if (f >= f0 && f < f1 && c.vac()[f] < 0) {
                     int slot = atomicAdd(&ic[f], 0x10000) >> 16;
-                    pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
+                    pool_w[slot] = w;
                 }
             }
+            __syncwarp();
+            // the keys in a dense pass over the pool: a draw per POOLED worker (an eighth of the workers at the default
+            // size), not a Philox block in every iteration of the pass over all of them
+            for (int i = lane; i < total; i += 32) pool_k[i] = c.d.fire_key(pool_w[i]);
             __syncwarp();
             for (int i = lane; i < total; i += 32) {
                 const int w = pool_w[i]; const unsigned key = pool_k[i];

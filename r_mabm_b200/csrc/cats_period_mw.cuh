@@ -507,10 +507,12 @@ __device__ void mw_fire(C &c)
                     const int f = ff[u], w = w0 + u * T;
                     if (f >= f0 && f < f1 && c.vac()[f] < 0) {
                         const int slot = atomicAdd(&ic[f], 0x10000) >> 16;
-                        pool_w[slot] = w; pool_k[slot] = c.d.fire_key(w);
+                        pool_w[slot] = w;
                     }
                 }
             }
+            __syncthreads();
+            for (int i = tid; i < total; i += T) pool_k[i] = c.d.fire_key(pool_w[i]);   // dense: one draw per pooled worker
             __syncthreads();
             for (int i = tid; i < total; i += T) {
                 const int w = pool_w[i]; const unsigned key = pool_k[i];

@@ -28,15 +28,18 @@ _lib = None
 
 
 def build() -> Path:
-    h = hashlib.sha1()
+    import os
+    extra = os.environ.get("CATS_EMU_EXTRA", "").split()   # development aid: extra -D flags for the emulated build
+    h = hashlib.sha1(" ".join(extra).encode())
     for p in _SOURCES:
         h.update(p.read_bytes())
     out = _BUILD / f"libcats_emu_{h.hexdigest()[:12]}.so"
     if not out.exists():
         _BUILD.mkdir(exist_ok=True)
-        for old in _BUILD.glob("libcats_emu_*.so"):
-            old.unlink()
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
+        if not extra:
+            for old in _BUILD.glob("libcats_emu_*.so"):
+                old.unlink()
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", *extra,
                         "-I/usr/local/cuda/include", "-o", str(out), str(_HERE / "cats_emu.cpp"),
                         str(_HERE / "simt_emu.cpp")], check=True)
     return out

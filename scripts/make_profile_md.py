@@ -11,6 +11,18 @@ unit = sys.argv[8] if len(sys.argv) > 8 else "economy-period"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h, u, r = rows[0], rows[1], rows[2]
+if kern == "auto":
+    # the exact mangled name of the kernel that was captured, from its demangled name in the report (a substring such
+    # as "ILi5ELi14ELi2ELb0ELi2" also matches the strict-mode instantiation and mixes two kernels' line tables)
+    dem = r[h.index("Kernel Name")]
+    mt = re.search(r"(cats_period_mw_kernel|cats_period_kernel)<([^>]*)>", dem)
+    if mt:
+        kinds = "iiibib" if mt.group(1) == "cats_period_kernel" else "iiiib"
+        args = [a.strip() for a in mt.group(2).split(",")]
+        kern = mt.group(1) + "I" + "".join(("Lb" if k == "b" else "Li") + a + "E" for k, a in zip(kinds, args)) + "E"
+    else:
+        kern = re.search(r"(cats_\w+)", dem).group(1)
+    print("kernel:", dem, "->", kern)
 m = {n: (r[i], u[i]) for i, n in enumerate(h)}
 def f(name): return float(m[name][0].replace(",", ""))
 def unit_bytes(name):
@@ -30,7 +42,7 @@ dur_us = f("gpu__time_duration.sum") * {"us": 1, "ms": 1e3, "ns": 1e-3, "second"
 dr, dw = unit_bytes("dram__bytes_read.sum"), unit_bytes("dram__bytes_write.sum")
 inst = f("smsp__inst_executed.sum")
 out = [f"# ncu --set full: {name} ({kern}), {tag}", "",
-       "Capture: scripts/r2_profile.sh (gpurun, 1 B200, each command directly after the same command exited 0 without ncu;",
+       "Capture: scripts/r3_profile.sh (gpurun, 1 B200, each command directly after the same command exited 0 without ncu;",
        "`ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1`).", "",
        f"Launch profiled: {what}",
        "Times under ncu are cold-cache and serialised: use shares, not absolutes.", "", "| metric | value |", "|---|---|"]

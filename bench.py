@@ -73,6 +73,9 @@ def parse():
     ap.add_argument("--economies", type=int, default=0, help="override the config's economy count")
     ap.add_argument("--burnin", type=int, default=BURNIN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-staged", action="store_true",
+                    help="e2e arm with explicit H2D / D2H copies through the staging block instead of the kernel "
+                         "working on the pinned host buffers in place (A/B aid)")
     return ap.parse_args()
 
 
@@ -354,6 +357,8 @@ def run_b200(args):
         def step_e2e():
             return env.step_host(h_actions, h_mask, want_stats=True)
         h2d, d2h = env.h2d_bytes_per_step() + B * nA, env.d2h_bytes_per_step(True)
+    if args.e2e_staged:
+        lib.cats_debug_set_host_zero_copy(int(os.environ.get("CATS_ZC_MODE", "0")))
     for _ in range(3):
         flush_l2(); step_e2e()
     barrier()
@@ -436,7 +441,10 @@ def run_b200(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, cfg, world, B, total, env.blob_bytes, flush),
             "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "transport": ("device-resident policy; the step's mean reward read on the host" if rollout is not None
+                                  else "explicit cudaMemcpyAsync through a device staging block" if args.e2e_staged
+                                  else "actions: one pinned H2D copy; outputs: written in place into pinned host buffers by the kernel over PCIe (cats_step_host)")},
             "gpu_launches": launches,
             "step_ms": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1], "mean": statistics.fmean(srt)},
             "timed_region_s": t_region,

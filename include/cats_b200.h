@@ -145,9 +145,13 @@ typedef struct cats_step_args {
  * _get_reward, _get_terminated and _get_obs, for B economies, n_periods times. */
 int cats_step(const cats_step_args *args);
 
-/* Same call with HOST action/obs/reward/terminated/stats buffers (pageable or pinned): copies
- * actions host->device, runs the step, copies the outputs back and synchronises the stream.
- * d_scratch must hold cats_host_scratch_bytes(B, n_agents, n_periods) device bytes. */
+/* Same call with HOST action/obs/reward/terminated/stats buffers (pageable or pinned) and a stream
+ * synchronisation at the end: the outputs are in the host buffers when it returns.  The actions are copied
+ * host->device ahead of the step.  Page-locked OUTPUT buffers (cudaHostAlloc / cudaHostRegister / torch
+ * pin_memory: mapped under unified addressing) are written IN PLACE: every economy posts its outputs over
+ * PCIe while the others are still computing, so no copy is left when the kernel ends.  Pageable output
+ * buffers are staged through d_scratch and copied out.  d_scratch must hold
+ * cats_host_scratch_bytes(B, n_agents, n_periods) device bytes either way. */
 size_t cats_host_scratch_bytes(int64_t B, int n_agents, int n_periods);
 /* Byte offsets of the seven sections of that staging block (actions, mask, obs, reward, terminated,
  * status, stats).  A caller whose HOST buffers sit at the same offsets inside one (pinned) block gets a
@@ -242,6 +246,11 @@ void cats_debug_set_warps(int warps_per_economy);
  * one-warp kernel's rounds, the others prepare households ahead of it), 0 = block-wide market, -1 = chosen per launch
  * (pipeline up to 256 sellers; default).  Results never depend on it. */
 void cats_debug_set_pipe(int mode);
+
+/* Debug aid: how cats_step_host treats page-locked host buffers.  Bit 0: the kernel reads the inputs in place; bit 1:
+ * it writes the outputs in place.  2 is the default (measured fastest); 0 stages both directions through d_scratch
+ * like pageable memory.  Results never depend on it. */
+void cats_debug_set_host_zero_copy(int mode);
 
 #ifdef __cplusplus
 }

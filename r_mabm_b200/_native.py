@@ -34,7 +34,7 @@ EXPORTS = [
     "cats_tape_bytes", "cats_tape_offsets", "cats_init", "cats_reset_masked", "cats_step", "cats_q_step", "cats_host_scratch_bytes",
     "cats_step_host", "cats_host_block_offsets", "cats_workset_bytes", "cats_workset_field_info", "cats_launch_info",
     "cats_launch_count", "cats_debug_phase_cycles", "cats_debug_set_group", "cats_debug_set_static",
-    "cats_debug_set_warps", "cats_debug_set_pipe", "cats_launch_shape",
+    "cats_debug_set_warps", "cats_debug_set_pipe", "cats_debug_set_host_zero_copy", "cats_launch_shape",
 ]
 
 
@@ -121,6 +121,8 @@ def load() -> C.CDLL:
     L.cats_debug_set_warps.restype = None
     L.cats_debug_set_pipe.argtypes = [C.c_int]
     L.cats_debug_set_pipe.restype = None
+    L.cats_debug_set_host_zero_copy.argtypes = [C.c_int]
+    L.cats_debug_set_host_zero_copy.restype = None
     if L.cats_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.cats_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = L

@@ -303,9 +303,11 @@ class BatchedCats:
 
     def step_host(self, actions_host: torch.Tensor | None, mask_host: torch.Tensor | None = None,
                   want_stats: bool = True):
-        """End-to-end step with HOST buffers (pinned recommended): host->device copy of the
-        actions, the period kernel, device->host copy of obs / reward / terminated / stats, one
-        stream sync.  This is the call bench.py times for `e2e`."""
+        """End-to-end step with HOST buffers: actions in, obs / reward / terminated / stats out, one stream
+        sync.  The buffers are this object's pinned block: one copy moves the actions in, and the kernel writes the
+        outputs in place over PCIe as each economy finishes (cats_step_host: zero copy for page-locked output
+        buffers, staged copies for pageable ones).  This is the
+        call bench.py times for `e2e`."""
         nA, B = self.n_agents, self.B
         self._ensure_host_block()
         a = self._args(1, self.flags if nA > 0 and actions_host is not None else self.flags | nat.FLAG_BURNIN,
@@ -324,6 +326,7 @@ class BatchedCats:
                 a.d_action_mask = self._h_mask_in.data_ptr()
             else:
                 a.d_action_mask = None
+        if nA > 0:      # a burn-in step (no actions) reports observation and reward too, as the reference's does
             a.d_obs = self._h_obs.data_ptr(); a.d_reward = self._h_rew.data_ptr()
         a.d_terminated = self._h_term.data_ptr(); a.d_status = self._h_status.data_ptr()
         a.d_stats = self._h_stats.data_ptr() if want_stats else None

@@ -154,20 +154,22 @@ class Cats:
             raise ValueError(
                 f"Number of actions ({len(actions)}) must be equal to the number of agents ({self.n_agents})")
         eng = self._engine
-        act_t = mask_t = None
+        h_act = h_mask = None
         if self.n_agents > 0 and not burnin:
-            vals, mask = self._h_act.numpy(), self._h_mask.numpy()
+            h_act, h_mask = eng.host_action_buffers()      # pinned views the library uploads with one copy
+            vals, mask = h_act.numpy(), h_mask.numpy()
             vals[...] = 1.0; mask[...] = 0
             for i, a in enumerate(actions):
                 if "dummy" in a:                           # cats.py:439-440
                     continue
                 vals[0, i, 0], vals[0, i, 1] = float(a[0]), float(a[1])
                 mask[0, i] = 1
-            act_t = self._d_act.copy_(self._h_act, non_blocking=True)
-            mask_t = self._d_mask.copy_(self._h_mask, non_blocking=True)
-        obs_t, rew_t, term_t, _ = eng.step(act_t, mask_t, burnin=burnin or self.n_agents == 0)
+        # ONE call, ONE synchronisation: the kernel writes obs / reward / terminated / status straight into pinned
+        # host memory (cats_step_host); the state mirror behind info / attributes is refreshed only when read
+        self._h_obs, self._h_rew, self._h_term, _ = eng.step_host(h_act, h_mask, want_stats=False)
+        self._h_status = eng._h_status
+        self._blob_stale = True
         self.t += 1
-        self._sync_host(obs_t, rew_t, term_t)      # ONE synchronisation per step: state + outputs to the host
         status = int(self._h_status[0])
         if status:
             import warnings
@@ -187,33 +189,23 @@ class Cats:
     # -- host mirror of the one economy: filled once per step / reset, read by obs / info ---------------
     def _alloc_host(self) -> None:
         import torch
-        eng, nA = self._engine, max(self.n_agents, 1)
-        pin = dict(pin_memory=True)
-        self._h_blob = torch.empty((eng.blob_bytes,), dtype=torch.uint8, **pin)
-        self._h_obs = torch.empty((1, nA, 2), dtype=torch.float64, **pin)
-        self._h_rew = torch.empty((1, nA), dtype=torch.float64, **pin)
-        self._h_term = torch.empty((1,), dtype=torch.uint8, **pin)
-        self._h_status = torch.empty((1,), dtype=torch.int32, **pin)
-        self._h_act = torch.ones((1, nA, 2), dtype=torch.float64, **pin)
-        self._h_mask = torch.zeros((1, nA), dtype=torch.uint8, **pin)
-        self._d_act = torch.ones((1, nA, 2), dtype=torch.float64, device=eng.device)
-        self._d_mask = torch.zeros((1, nA), dtype=torch.uint8, device=eng.device)
+        eng = self._engine
+        self._h_blob = torch.empty((eng.blob_bytes,), dtype=torch.uint8, pin_memory=True)
         self._h_views: dict = {}
+        self._blob_stale = True
 
-    def _sync_host(self, obs_t=None, rew_t=None, term_t=None) -> None:
+    def _sync_host(self) -> None:
+        """Refresh the host mirror of the economy's state (one 37 KB copy at the default size)."""
         import torch
         eng = self._engine
         self._h_blob.copy_(eng.blobs[0], non_blocking=True)
-        if obs_t is not None and self.n_agents:
-            self._h_obs[:, :self.n_agents].copy_(obs_t, non_blocking=True)
-            self._h_rew[:, :self.n_agents].copy_(rew_t, non_blocking=True)
-        if term_t is not None:
-            self._h_term.copy_(term_t, non_blocking=True)
-        self._h_status.copy_(eng._status, non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
+        self._blob_stale = False
 
     def _field(self, name):
         """Host view of a named state field of the economy, as of the last step / reset."""
+        if self._blob_stale:
+            self._sync_host()
         v = self._h_views.get(name)
         if v is None:
             from .. import _native as nat

@@ -183,6 +183,51 @@ def test_step_host_equals_device_step():
     assert torch.equal(a.blobs, b.blobs)
 
 
+def test_step_host_zero_copy_staged_and_pageable_agree():
+    """cats_step_host works on mapped page-locked buffers in place (the kernel reads the actions and posts its outputs
+    over PCIe); pageable buffers, or the debug switch, go through the staging block.  Same bits every way."""
+    import ctypes as C
+    from r_mabm_b200 import _native as nat
+    B, A = 37, 2
+    envs = [_env(B, n_agents=A, seed=67) for _ in range(5)]
+    for e in envs: e.run(12)
+    g = torch.Generator().manual_seed(5)
+    lib = envs[0]._lib
+    for step in range(3):
+        acts = 0.9 + 0.2 * torch.rand((B, A, 2), dtype=torch.float64, generator=g)
+        mask = (torch.rand((B, A), generator=g) > 0.3).to(torch.uint8)
+        outs = []
+        # 0: pinned, outputs in place (default); 1: pinned, staged both ways; 4: pinned, inputs and outputs in place;
+        # 2: pageable caller buffers through the C-ABI; 3: device step
+        o = envs[0].step_host(acts.pin_memory(), mask.pin_memory(), want_stats=True)
+        outs.append([t.clone() for t in o])
+        for env_i, mode in ((1, 0), (4, 3)):
+            lib.cats_debug_set_host_zero_copy(mode)
+            try:
+                o = envs[env_i].step_host(acts.pin_memory(), mask.pin_memory(), want_stats=True)
+                outs.append([t.clone() for t in o])
+            finally:
+                lib.cats_debug_set_host_zero_copy(2)
+        e = envs[2]
+        e._ensure_host_block()
+        h_obs = torch.empty((B, A, 2), dtype=torch.float64); h_rew = torch.empty((B, A), dtype=torch.float64)
+        h_term = torch.empty((B,), dtype=torch.uint8); h_stats = torch.empty((B, 1, nat.N_STATS), dtype=torch.float64)
+        args = e._args(1, e.flags, want_io=False)
+        args.d_actions, args.d_action_mask = acts.data_ptr(), mask.data_ptr()
+        args.d_obs, args.d_reward, args.d_terminated = h_obs.data_ptr(), h_rew.data_ptr(), h_term.data_ptr()
+        args.d_status, args.d_stats = None, h_stats.data_ptr()
+        nat.check(lib.cats_step_host(C.byref(args), e._host_scratch.data_ptr()))
+        outs.append([h_obs, h_rew, h_term, h_stats])
+        do, dr, dt, ds = envs[3].step(acts.cuda(), mask.cuda(), want_stats=True)
+        torch.cuda.synchronize()
+        ref = [do.cpu(), dr.cpu(), dt.cpu(), ds.cpu()]
+        for k, got in enumerate(outs):
+            for x, y in zip(got, ref):
+                assert torch.equal(x, y), f"step {step}, path {k}"
+    for e in envs:
+        assert torch.equal(e.blobs, envs[3].blobs)
+
+
 def test_full_size_invariants_1024_economies():
     """BASELINE.json config 2 at full width: properties that need no oracle (MODEL.md section 6)."""
     B, W, F, N = 1024, 1000, 100, 20

@@ -416,29 +416,40 @@ __device__ void phase_fire(C &c, int limit)
             continue;
         }
         if (total > 0) {
-            int fnext = lane < W ? c.Oc()[lane] : -1;
-#pragma unroll 1
-            for (int w = lane; w < W; w += 32) {
-                const int f = fnext;
-                fnext = w + 32 < W ? c.Oc()[w + 32] : -1;   // next load in flight while this worker is handled
-                if (f >= f0 && f < f1 && c.vac()[f] < 0) {
-                    int slot = atomicAdd(&ic[f], 0x10000) >> 16;
-                    pool_w[slot] = w;
+            // the pass over the employment links: four workers per lane and load (the row is padded to 16 bytes), two
+            // loads in flight -- the pass waits on L2 a quarter as often as a link per lane would.  A pool entry is
+            // worker | employer << 16, so the ranking below need not read the link again.
+            const int4 *Oc4 = reinterpret_cast<const int4 *>(c.Oc());
+            const int nq = (W + 3) >> 2;
+            auto pool = [&](int f, int w) {
+                if (f >= f0 && f < f1 && w < W && c.vac()[f] < 0) {
+                    const int slot = atomicAdd(&ic[f], 0x10000) >> 16;
+                    pool_w[slot] = w | (f << 16);
                 }
+            };
+            const int4 none = make_int4(-1, -1, -1, -1);
+            int4 q0 = lane < nq ? Oc4[lane] : none, q1 = lane + 32 < nq ? Oc4[lane + 32] : none;
+#pragma unroll 1
+            for (int q = lane; q < nq; q += 32) {
+                const int4 v = q0;
+                q0 = q1;
+                q1 = q + 64 < nq ? Oc4[q + 64] : none;
+                const int w = q << 2;
+                pool(v.x, w); pool(v.y, w + 1); pool(v.z, w + 2); pool(v.w, w + 3);
             }
             __syncwarp();
             // the keys in a dense pass over the pool: a draw per POOLED worker (an eighth of the workers at the default
             // size), not a Philox block in every iteration of the pass over all of them
-            for (int i = lane; i < total; i += 32) pool_k[i] = c.d.fire_key(pool_w[i]);
+            for (int i = lane; i < total; i += 32) pool_k[i] = c.d.fire_key(pool_w[i] & 0xffff);
             __syncwarp();
             for (int i = lane; i < total; i += 32) {
-                const int w = pool_w[i]; const unsigned key = pool_k[i];
-                const int f = c.Oc()[w];
+                const int e = pool_w[i]; const unsigned key = pool_k[i];
+                const int w = e & 0xffff, f = e >> 16;
                 const int v = ic[f];
                 const int end = v >> 16, beg = end - (v & 0xffff);
                 int rank = 0;
                 for (int j = beg; j < end; ++j) {
-                    const unsigned kj = pool_k[j]; const int wj = pool_w[j];
+                    const unsigned kj = pool_k[j]; const int wj = pool_w[j] & 0xffff;
                     rank += (kj < key || (kj == key && wj < w)) ? 1 : 0;
                 }
                 if (rank < -c.vac()[f]) c.Oc()[w] = -1;
@@ -991,6 +1002,17 @@ __device__ __forceinline__ void goods_prepare(C &c, const Mkt &mkt, int z, int h
 template <int ZM, class C>
 __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long long *acc, int h, double pa, double b, GoodsList<C> cl);
 
+// The peer table of rule R2 (one word per seller, in the firing / capital-market scratch, idle during the goods
+// market): in a round with uncertain lanes, the mask of the lanes whose terminal the seller is; zero between rounds.
+template <class C>
+__device__ __forceinline__ int *goods_peer_table(const C &c) { return c.iat(c.layout().s_ic); }
+template <class C>
+__device__ __forceinline__ void goods_peer_table_init(const C &c, int first, int stride)
+{
+    int *tab = goods_peer_table(c);
+    for (int f = first; f < c.layout().F; f += stride) tab[f] = 0;
+}
+
 template <int ZM, class C>
 __device__ void phase_goods_market(C &c)
 {
@@ -1002,6 +1024,7 @@ __device__ void phase_goods_market(C &c)
     OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord; ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
     volatile double *gk = c.gk();
     if (lane == 0) goods_constants(c);
+    goods_peer_table_init(c, lane, 32);
     __syncwarp();
     const int nch = (H + 31) / 32;
 
@@ -1100,16 +1123,17 @@ __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long
             unsigned rem = has ? (peers & lt) : 0u;
             double ys = 0.0;
             if (has) ys = mkt.yr[term].x;
-            bool sold = false;
-            int esrc = 0;   // the lane that empties my seller before my turn (if sold)
+            int esrc = -1;   // the lane that empties my seller before my turn (>= 0: sold out when I get there)
             while (__any_sync(FULL, rem != 0u)) {
-                const int src = __ffs(rem) - 1;   // -1 (no peer left) reads lane 31: the value is not used then
+                // branch-free body: a lane without peers left reads lane 31 and changes nothing
+                const int src = __ffs(rem) - 1;
                 const double di = __shfl_sync(FULL, d_t, src);
-                if (rem) {
-                    rem &= rem - 1;
-                    if (ys > di) ys = ys - di; else { sold = true; esrc = src; rem = 0u; }   // sold out before my turn: stop replaying
-                }
+                const bool act = rem != 0u, more = act && ys > di;
+                if (act && !more) esrc = src;            // sold out before my turn: stop replaying
+                rem = more ? (rem & (rem - 1u)) : 0u;
+                ys = more ? ys - di : ys;
             }
+            const bool sold = esrc >= 0;
             const bool full = has && !sold && ys > d_t;
             // ---- who may commit (rule R2, cats_period_mw.cuh): a lane that exhausts its seller or finds it sold out
             // walks on -- to one of the sellers left on its list; lanes above it whose terminal is on that list
@@ -1118,24 +1142,31 @@ __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long
             const unsigned movers = __ballot_sync(FULL, has && (sold || !full));
             bool endangered = false;
             if (movers) {
-                // only lanes that could still commit a purchase matter (`open`), and only uncertain lanes BELOW the
-                // highest of them can endanger one: most lanes queued behind a sell-out drop out of the loop
+                // The lanes at a seller post their peer mask under the seller's row (one plain store each: the peers
+                // write the same word); an uncertain lane ORs the rows of the sellers left on its list -- the lanes
+                // it endangers, all at once -- and one OR-reduction over the warp gives every endangered lane.  One
+                // pass per level of the cascade instead of one per uncertain lane.  The rows are zero between rounds.
+                int *tab = goods_peer_table(c);
+                if (has) tab[term] = (int)peers;
+                __syncwarp();
                 const unsigned fullm = __ballot_sync(FULL, full);
-                unsigned open = __ballot_sync(FULL, has && !sold);
-                unsigned unc = movers, todo = movers;
-                while (open) {
-                    todo &= (1u << (31 - __clz((int)open))) - 1u;   // below the highest open lane
-                    if (!todo) break;
-                    const int i = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const auto li = cl.from_lane(i);
-                    const bool hit = has && !sold && !endangered && lane > i && li.contains(term);
-                    endangered |= hit;
-                    const unsigned hitm = __ballot_sync(FULL, hit);
-                    open &= ~hitm;
-                    const unsigned newly = hitm & fullm & ~unc;
-                    unc |= newly; todo |= newly;
-                }
+                const unsigned openm = __ballot_sync(FULL, has && !sold);
+                unsigned unc = movers, fresh = movers, endm = 0u;
+                do {
+                    unsigned v = 0u;
+                    if ((fresh >> lane) & 1u) {
+                        auto li = cl;
+#pragma unroll
+                        for (int k = 0; k < ZM - 1; ++k) { int sl; if (li.pop(sl)) v |= (unsigned)tab[sl]; }
+                        v &= ~(lt | (1u << lane));   // the lanes above me
+                    }
+                    const unsigned hits = __reduce_or_sync(FULL, v) & openm & ~endm;
+                    endm |= hits;
+                    fresh = hits & fullm & ~unc;
+                    unc |= fresh;
+                } while (fresh);
+                endangered = (endm >> lane) & 1u;
+                if (has) tab[term] = 0;   // (every read of the table is behind the last reduction)
             }
             const unsigned commit = __ballot_sync(FULL, mine && (!has || (!sold && !endangered)));
             const bool cm = (commit >> lane) & 1u;

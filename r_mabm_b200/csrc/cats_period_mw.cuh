@@ -355,6 +355,7 @@ __device__ void mw_goods_market_pc(C &c)
     OrderT<C::kStatic ? DefaultLayout::kW + DefaultLayout::kF + DefaultLayout::kN : 0, !C::kProd> ord;
     if (warp == 0) {
         ord.init(c.d, MKT_GOODS, c.a->od[MKT_GOODS], c.okeys(), lane);
+        goods_peer_table_init(c, lane, 32);
         if (lane == 0) {
             goods_constants(c);
             for (int s = 0; s < S; ++s) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }

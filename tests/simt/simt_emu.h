@@ -79,7 +79,7 @@ inline void yield() { simt_switch(&g_cur->sp, g_blk->sched_sp); }
     abort();
 }
 
-enum { K_SYNC, K_SHFL, K_BALLOT, K_MATCH };
+enum { K_SYNC, K_SHFL, K_BALLOT, K_MATCH, K_REDUCE_OR };
 
 inline uint64_t collective(int kind, uint64_t v, uint64_t v2, void (*complete)(Warp &, uint64_t *))
 {
@@ -164,6 +164,15 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
     return (unsigned)simt::collective(simt::K_BALLOT, pred ? 1 : 0, 0, [](simt::Warp &w, uint64_t *out) {
         unsigned b = 0;
         for (int l = 0; l < 32; ++l) if (((w.present >> l) & 1u) && w.in[l]) b |= 1u << l;
+        for (int l = 0; l < 32; ++l) out[l] = b;
+    });
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    simt::check_mask(mask);
+    return (unsigned)simt::collective(simt::K_REDUCE_OR, v, 0, [](simt::Warp &w, uint64_t *out) {
+        unsigned b = 0;
+        for (int l = 0; l < 32; ++l) if ((w.present >> l) & 1u) b |= (unsigned)w.in[l];
         for (int l = 0; l < 32; ++l) out[l] = b;
     });
 }

@@ -244,7 +244,7 @@ void cats_debug_set_warps(int warps_per_economy);
 
 /* Debug aid: the goods market of the multi-warp kernel: 1 = producer / consumer pipeline (one warp commits with the
  * one-warp kernel's rounds, the others prepare households ahead of it), 0 = block-wide market, -1 = chosen per launch
- * (pipeline up to 256 sellers; default).  Results never depend on it. */
+ * (the pipeline; default).  Results never depend on it. */
 void cats_debug_set_pipe(int mode);
 
 /* Debug aid: how cats_step_host treats page-locked host buffers.  Bit 0: the kernel reads the inputs in place; bit 1:

@@ -86,13 +86,14 @@ static int choose_group(const Layout &L, long long B, int sms)
 // long as ONE economy's dependent chain, so several warps share an economy instead (cats_period_mw.cuh): as many as
 // keep ~28 warps on every SM, if the block's shared memory still lets every economy of the launch be resident.
 // the multi-warp kernel's goods market: a pipeline (producer warps prepare, one warp commits with the one-warp
-// kernel's rounds) where sellers are few, the block-wide market (cats_period_mw.cuh) where they are many
-// (measured, DESIGN.md 2.7: 1,024 default-size economies at 4 warps: pipeline 7.99e6, block-wide 7.41e6; one economy
-// per SM at 8 warps: block-wide 99.8 us, pipeline 104.7 us; 10x economy: no difference)
-static bool choose_pipe(const Layout &L, int nw)
+// kernel's rounds) or the block-wide market (cats_period_mw.cuh).  Since the one-warp rounds find the endangered lanes
+// through the peer table the pipeline is the faster one at every size measured (1,024 default-size
+// economies at 4 warps: 8.26e6 against 7.38e6; 256 economies of 10x size at 8 warps: 3.35e5 against 3.21e5; one
+// default-size economy per SM at 8 warps: equal); the block-wide market stays selectable (cats_debug_set_pipe).
+static bool choose_pipe(const Layout &, int)
 {
     const int forced = g_pipe.load();
-    return forced >= 0 ? forced != 0 : (L.F <= 256 && nw <= 4);
+    return forced >= 0 ? forced != 0 : true;
 }
 
 static int choose_warps(const Layout &L, long long B, int sms)
@@ -109,7 +110,9 @@ static int choose_warps(const Layout &L, long long B, int sms)
         const int nw = cand[i];
         if (want < nw) continue;
         const long long bytes = slice_bytes(L) + mw_extra_bytes(nw, L.F) + 1024;
-        const long long fit = (228 * 1024) / bytes;
+        long long fit = (228 * 1024) / bytes;
+        const long long by_regs = nw == 8 ? 3 : 7;   // blocks per SM the kernels' __launch_bounds__ are cut for (cats_inst_mw.cu)
+        if (fit > by_regs) fit = by_regs;
         if (bytes <= 227 * 1024 && fit * sms >= B) return nw;
     }
     return 1;

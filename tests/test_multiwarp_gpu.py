@@ -43,8 +43,9 @@ def test_default_size_120_periods(lib, warps, pipe):
 
 @pytest.mark.parametrize("W,F,N,zs,warps", [(37, 3, 1, (5, 2, 5), 2), (1, 1, 1, (5, 2, 5), 4), (64, 33, 31, (8, 8, 8), 8),
                                              (130, 7, 2, (2, 1, 3), 4), (500, 50, 10, (4, 3, 6), 8)])
-def test_ragged_sizes(lib, W, F, N, zs, warps):
-    lib.cats_debug_set_warps(warps)
+@pytest.mark.parametrize("pipe", [0, 1])
+def test_ragged_sizes(lib, W, F, N, zs, warps, pipe):
+    lib.cats_debug_set_warps(warps); lib.cats_debug_set_pipe(pipe)
     p = dict(orc.DEFAULT_PARAMS, z_c=zs[0], z_k=zs[1], z_e=zs[2])
     env = _env(3, W=W, F=F, N=N, params=dict(p), seed=41)
     orcs = make_oracles(3, W, F, N, params=p, seed=41)

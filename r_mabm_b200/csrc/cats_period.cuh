@@ -1169,25 +1169,18 @@ __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long
                 if (has) tab[term] = 0;   // (every read of the table is behind the last reduction)
             }
             const unsigned commit = __ballot_sync(FULL, mine && (!has || (!sold && !endangered)));
+            // branch-free: a FULL lane buys d_t, an EXHAUST lane takes what is left and walks on with the rest of its
+            // budget, a lane queued behind a seller that is now empty for good walks on, everybody else keeps its state
             const bool cm = (commit >> lane) & 1u;
-            bool done = false;
-            if (cm) {
-                if (!has) done = true;                    // nothing left to visit: the rest of b is saved
-                else {
-                    const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
-                    const int seller = term;
-                    if (full) { ys = ys - d_t; b = 0.0; done = true; }
-                    else {                                 // takes what is left, then walks on
-                        b = b - ys * mkt.p[seller]; ys = 0.0;
-                        term = b > 0.0 ? TERM_WALK : TERM_NONE;
-                        done = term == TERM_NONE;
-                        if constexpr (!C::kStrict) xb = fx_from(b * rpavg);
-                    }
-                    if (lastp) mkt.yr[seller].x = ys;
-                }
-            } else if (sold && ((commit >> esrc) & 1u)) {
-                term = TERM_WALK;                          // queued behind a lane that emptied the seller for good
-            }
+            const bool buy = cm && has, exh = buy && !full;
+            const bool lastp = (peers & commit & ~lt & ~(1u << lane)) == 0u;   // last committing lane at this seller
+            const double left = exh ? b - ys * mkt.p[term] : 0.0;              // EXHAUST: the budget that remains
+            if (buy && lastp) mkt.yr[term].x = full ? ys - d_t : 0.0;
+            if (buy) b = left;
+            if constexpr (!C::kStrict) { if (exh) xb = fx_from(left * rpavg); }
+            const bool walk_on = (exh && left > 0.0) || (!cm && sold && ((commit >> esrc) & 1u));
+            const bool done = cm && !(exh && left > 0.0);
+            term = walk_on ? TERM_WALK : (done ? TERM_NONE : term);
             pend &= ~__ballot_sync(FULL, done);
             __syncwarp();
         }

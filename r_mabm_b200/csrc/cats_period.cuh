@@ -27,6 +27,7 @@
 #define CATS_PERIOD_CUH
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/cats_b200.h"
 #include "cats_device.cuh"
@@ -733,6 +734,67 @@ __device__ void phase_produce(C &c)
 // a12 capital_goods_market! (cats.py:387).  The investing C-firms are compacted in visiting order;
 // 32 of them at a time draw and price-sort their z_k suppliers in parallel and then trade one after
 // the other (there are ~F * Iprob buyers per period: a short chain).
+// a12, one buyer: down its price-sorted candidates while it has funds and wants capital.  kd: capital still wanted,
+// cb: funds, lq: liquidity; iv / vi: capital bought and its value.  Sequential per supplier (see capital_go).
+template <int ZM, bool STRICT>
+__device__ __forceinline__ void capital_trade(int z, const int (&cand)[ZM], const double (&pr)[ZM], const double *RPk, double *Ydk,
+                                              double *Ysk, double &kd, double &cb, double &lq, double &iv, double &vi)
+{
+#pragma unroll
+    for (int k = 0; k < ZM; ++k) {
+        if (k < z && cb > 0.0 && kd > 0.0) {
+            const int best = cand[k];
+            const double pk = pr[k], rpk = RPk[best];
+            const double afford = STRICT ? cb / pk : cb * rpk;
+            const double want = afford < kd ? afford : kd;
+            Ydk[best] = Ydk[best] + want;
+            const double ys = Ysk[best];
+            if (ys > 0.0) {
+                const double full = kd * pk;
+                const double spend = cb < full ? cb : full;
+                const double q = STRICT ? spend / pk : spend * rpk;
+                if (ys > q) {
+                    Ysk[best] = ys - q;
+                    kd = kd - q; cb = cb - spend;
+                    lq = lq - spend; iv = iv + q; vi = vi + spend;
+                } else {
+                    const double cost = ys * pk;
+                    kd = kd - ys; cb = cb - cost;
+                    lq = lq - cost;
+                    iv = iv + ys; vi = vi + cost;
+                    Ysk[best] = 0.0;
+                }
+            }
+        }
+    }
+}
+// Buyers trade in visiting order -- but only buyers that share a supplier have to.  Every lane marks its candidates in
+// a 32-bit set (supplier mod 32: a false match only delays a lane); a pending lane (bit in m) may trade as soon as no
+// pending lane BELOW it has a candidate in common.  The lowest pending lane always may, so rounds end; each round takes
+// every buyer whose suppliers are its own for now: ~6 rounds for the ~25 buyers of a default-size period.  Warp collective.
+// SetT: unsigned (supplier mod 32; exact up to 32 suppliers: the default configuration has 20) or unsigned long long
+// (mod 64) for the instantiations that serve any size.
+template <class SetT, int ZM>
+__device__ __forceinline__ SetT capital_set(const int (&cand)[ZM], int z)
+{
+    SetT cset = 0;
+#pragma unroll
+    for (int k = 0; k < ZM; ++k) if (k < z) cset |= (SetT)1 << (cand[k] & (int)(8 * sizeof(SetT) - 1));
+    return cset;
+}
+template <class SetT>
+__device__ __forceinline__ bool capital_go(unsigned m, SetT cset, int lane)
+{
+    const bool pend = (m >> lane) & 1u;
+    SetT below = pend ? cset : (SetT)0;   // becomes the union over the pending lanes up to this one ...
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const SetT t = __shfl_up_sync(FULL, below, off); if (lane >= off) below |= t; }
+    below = __shfl_up_sync(FULL, below, 1);   // ... and now strictly below it
+    if (lane == 0) below = 0;
+    return pend && (cset & below) == 0;
+}
+template <class C> using CapitalSet = std::conditional_t<C::kStatic, unsigned, unsigned long long>;
+
 template <int ZM, class C>
 __device__ void phase_capital_market(C &c)
 {
@@ -771,37 +833,14 @@ __device__ void phase_capital_market(C &c)
             sort_by_price<ZM>(cand, pr, z);
         }
         unsigned m = __ballot_sync(FULL, act);
+        using SetT = CapitalSet<C>;
+        const SetT cset = act ? capital_set<SetT, ZM>(cand, z) : (SetT)0;
         while (m) {
-            const int l = __ffs(m) - 1; m &= m - 1;
-            if (lane == l) {
+            const bool go = capital_go(m, cset, lane);
+            m &= ~__ballot_sync(FULL, go);
+            if (go) {
                 double iv = 0.0, vi = 0.0;   // produce zeroed investment and its value this period
-#pragma unroll
-                for (int k = 0; k < ZM; ++k) {
-                    if (k < z && cb > 0.0 && kd > 0.0) {
-                        const int best = cand[k];
-                        const double pk = pr[k], rpk = RPk[best];
-                        const double afford = C::kStrict ? cb / pk : cb * rpk;
-                        const double want = afford < kd ? afford : kd;
-                        Ydk[best] = Ydk[best] + want;
-                        const double ys = Ysk[best];
-                        if (ys > 0.0) {
-                            const double full = kd * pk;
-                            const double spend = cb < full ? cb : full;
-                            const double q = C::kStrict ? spend / pk : spend * rpk;
-                            if (ys > q) {
-                                Ysk[best] = ys - q;
-                                kd = kd - q; cb = cb - spend;
-                                lq = lq - spend; iv = iv + q; vi = vi + spend;
-                            } else {
-                                const double cost = ys * pk;
-                                kd = kd - ys; cb = cb - cost;
-                                lq = lq - cost;
-                                iv = iv + ys; vi = vi + cost;
-                                Ysk[best] = 0.0;
-                            }
-                        }
-                    }
-                }
+                capital_trade<ZM, C::kStrict>(z, cand, pr, RPk, Ydk, Ysk, kd, cb, lq, iv, vi);
                 liq[f] = lq; inv[f] = iv; valinv[f] = vi; Kdem[f] = kd;
             }
             __syncwarp();

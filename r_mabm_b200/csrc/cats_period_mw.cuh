@@ -761,35 +761,35 @@ __device__ void mw_capital_market(C &c)
             for (int k = 0; k < ZM; ++k) { r.cand[k] = cand[k]; r.pr[k] = pr[k]; }
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int i = 0; i < nb; ++i) {
-                CapRec<ZM> &r = rec[i];
-                double kd = r.kd, cb = r.cb, lq = r.lq, iv = 0.0, vi = 0.0;
-                for (int k = 0; k < z && cb > 0.0 && kd > 0.0; ++k) {
-                    const int best = r.cand[k];
-                    const double pk = r.pr[k], rpk = RPk[best];
-                    const double afford = cb * rpk;
-                    const double want = afford < kd ? afford : kd;
-                    Ydk[best] = Ydk[best] + want;
-                    const double ys = Ysk[best];
-                    if (ys > 0.0) {
-                        const double full = kd * pk;
-                        const double spend = cb < full ? cb : full;
-                        const double q = spend * rpk;
-                        if (ys > q) {
-                            Ysk[best] = ys - q;
-                            kd = kd - q; cb = cb - spend;
-                            lq = lq - spend; iv = iv + q; vi = vi + spend;
-                        } else {
-                            const double cost = ys * pk;
-                            kd = kd - ys; cb = cb - cost;
-                            lq = lq - cost;
-                            iv = iv + ys; vi = vi + cost;
-                            Ysk[best] = 0.0;
-                        }
-                    }
+        if (c.warp == 0) {
+            // one warp trades the records, 32 at a time, in rounds of buyers that share no supplier (capital_go)
+            for (int base = 0; base < nb; base += 32) {
+                const int i = base + lane;
+                const bool act = i < nb;
+                int cand[ZM]; double pr[ZM];
+                double kd = 0.0, cb = 0.0, lq = 0.0;
+#pragma unroll
+                for (int k = 0; k < ZM; ++k) { cand[k] = 0; pr[k] = 0.0; }
+                if (act) {
+                    const CapRec<ZM> &r = rec[i];
+                    kd = r.kd; cb = r.cb; lq = r.lq;
+#pragma unroll
+                    for (int k = 0; k < ZM; ++k) { cand[k] = r.cand[k]; pr[k] = r.pr[k]; }
                 }
-                r.kd = kd; r.lq = lq; r.iv = iv; r.vi = vi;
+                unsigned m = __ballot_sync(FULL, act);
+                using SetT = CapitalSet<C>;
+                const SetT cset = act ? capital_set<SetT, ZM>(cand, z) : (SetT)0;
+                while (m) {
+                    const bool go = capital_go(m, cset, lane);
+                    m &= ~__ballot_sync(FULL, go);
+                    if (go) {
+                        double iv = 0.0, vi = 0.0;
+                        capital_trade<ZM, false>(z, cand, pr, RPk, Ydk, Ysk, kd, cb, lq, iv, vi);
+                        CapRec<ZM> &r = rec[i];
+                        r.kd = kd; r.lq = lq; r.iv = iv; r.vi = vi;
+                    }
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();

@@ -24,5 +24,5 @@ def probe(B, periods, warps, pipe, burn=300, reps=3):
 
 Bs = [int(x) for x in sys.argv[1:]] or [1024, 2048, 3072, 4096]
 for B in Bs:
-    for warps, pipe in ((1, -1), (4, 0), (4, 1), (8, 0), (8, 1)):
+    for warps, pipe in ((1, -1), (2, 1), (4, 1), (8, 1)):
         probe(B, 20, warps, pipe)

@@ -27,7 +27,7 @@ STAT_NAMES = ["Y_real", "wb", "Un", "bankruptcy_rate", "avg_price", "Y_nominal_t
               "inflationRate", "consumption", "totK", "dividendsB", "profitsB", "GB", "deficitGDP",
               "bonds", "price_k"]
 
-# every symbol include/cats_b200.h declares (tests/test_abi.py checks the .so exports them all)
+# every symbol include/cats_b200.h and include/cats_b200_debug.h declare (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "cats_abi_version", "cats_last_error", "cats_blob_bytes", "cats_field_info", "cats_field_name",
     "cats_field_stride",

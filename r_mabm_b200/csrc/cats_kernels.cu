@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "cats_period.cuh"
+#include "../../include/cats_b200_debug.h"
 
 #include "cats_aux.cuh"
 #include "cats_period_mw.cuh"

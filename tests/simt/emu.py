@@ -23,7 +23,7 @@ _HERE = Path(__file__).resolve().parent
 _CSRC = _HERE.parent.parent / "r_mabm_b200" / "csrc"
 _BUILD = _HERE / "_build"
 _SOURCES = [_HERE / "cats_emu.cpp", _HERE / "simt_emu.cpp", _HERE / "simt_emu.h"] + sorted(_CSRC.glob("*.cuh")) + \
-    sorted(_CSRC.glob("*.h")) + [_HERE.parent.parent / "include" / "cats_b200.h"]
+    sorted(_CSRC.glob("*.h")) + sorted((_HERE.parent.parent / "include").glob("*.h"))
 _lib = None
 
 

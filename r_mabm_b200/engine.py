@@ -48,6 +48,8 @@ class BatchedCats:
         if not torch.cuda.is_available():
             raise RuntimeError("r_mabm_b200 needs a CUDA device: there is no CPU fallback")
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.B, self.W, self.F, self.N, self.H = B, W, F, N, W + F + N
         self.n_agents = n_agents
         self.reward_type, self.price_change, self.log_mode = reward_type, price_change, log_mode
@@ -92,6 +94,7 @@ class BatchedCats:
         self._i32 = self._blob.view(torch.int32)
         self._views: dict[str, torch.Tensor] = {}
         self._host_scratch = None
+        self._host_call_cache: dict = {}   # step_host: argument blocks by call shape
         self.periods_done = 0
         self.reset_state()
 
@@ -310,30 +313,43 @@ class BatchedCats:
         call bench.py times for `e2e`."""
         nA, B = self.n_agents, self.B
         self._ensure_host_block()
-        a = self._args(1, self.flags if nA > 0 and actions_host is not None else self.flags | nat.FLAG_BURNIN,
-                       want_io=False)
-        if nA > 0 and actions_host is not None:
+        acting = nA > 0 and actions_host is not None
+        if acting:
             if tuple(actions_host.shape) != (B, nA, 2) or actions_host.dtype != torch.float64 or actions_host.is_cuda:
                 raise ValueError("actions_host must be a float64 CPU tensor of shape [B, n_agents, 2]")
             # staged through the pinned block (a host-to-host copy of a few hundred KB) unless the caller
             # already wrote into the block's own views (`host_action_buffers`)
             if actions_host.data_ptr() != self._h_act_in.data_ptr():
                 self._h_act_in.copy_(actions_host)
-            a.d_actions = self._h_act_in.data_ptr()
-            if mask_host is not None:
-                if mask_host.data_ptr() != self._h_mask_in.data_ptr():
-                    self._h_mask_in.copy_(mask_host)
-                a.d_action_mask = self._h_mask_in.data_ptr()
-            else:
-                a.d_action_mask = None
-        if nA > 0:      # a burn-in step (no actions) reports observation and reward too, as the reference's does
-            a.d_obs = self._h_obs.data_ptr(); a.d_reward = self._h_rew.data_ptr()
-        a.d_terminated = self._h_term.data_ptr(); a.d_status = self._h_status.data_ptr()
-        a.d_stats = self._h_stats.data_ptr() if want_stats else None
-        with torch.cuda.device(self.device):
-            nat.check(self._lib.cats_step_host(C.byref(a), self._host_scratch.data_ptr()))
+            if mask_host is not None and mask_host.data_ptr() != self._h_mask_in.data_ptr():
+                self._h_mask_in.copy_(mask_host)
+        # The argument block of a call shape is built once: at a few thousand economies per GPU the step is ~150 us and
+        # the Python side of the call is what is left to trim.
+        flags = self.flags if acting else self.flags | nat.FLAG_BURNIN
+        key = (flags, acting, acting and mask_host is not None, want_stats, self._stream(), self._host_scratch.data_ptr(),
+               self.seed, self.economy_base, self.bankruptcy_reward)
+        hit = self._host_call_cache.get(key)
+        if hit is None:
+            a = self._args(1, flags, want_io=False)
+            if acting:
+                a.d_actions = self._h_act_in.data_ptr()
+                a.d_action_mask = self._h_mask_in.data_ptr() if mask_host is not None else None
+            if nA > 0:      # a burn-in step (no actions) reports observation and reward too, as the reference's does
+                a.d_obs = self._h_obs.data_ptr(); a.d_reward = self._h_rew.data_ptr()
+            a.d_terminated = self._h_term.data_ptr(); a.d_status = self._h_status.data_ptr()
+            a.d_stats = self._h_stats.data_ptr() if want_stats else None
+            hit = (a, C.byref(a), self._host_scratch.data_ptr(),
+                   (self._h_obs[:, :nA], self._h_rew[:, :nA], self._h_term, self._h_stats if want_stats else None))
+            if len(self._host_call_cache) > 16:
+                self._host_call_cache.clear()
+            self._host_call_cache[key] = hit
+        if torch.cuda.current_device() == self.device.index:
+            nat.check(self._lib.cats_step_host(hit[1], hit[2]))
+        else:
+            with torch.cuda.device(self.device):
+                nat.check(self._lib.cats_step_host(hit[1], hit[2]))
         self.periods_done += 1
-        return self._h_obs[:, :nA], self._h_rew[:, :nA], self._h_term, (self._h_stats if want_stats else None)
+        return hit[3]
 
     def host_action_buffers(self):
         """Pinned host views [B, n_agents, 2] float64 and [B, n_agents] uint8 inside the staging block:

@@ -112,3 +112,18 @@ def test_config2_width_auto_shape_matches_one_warp_kernel(lib):
     for i, o in zip(ids, orcs):
         assert np.array_equal(bits(a.field("PA")[i].cpu().numpy()), bits(o.f64("PA")))
         assert np.array_equal(a.field("Oc")[i].cpu().numpy(), o.i32("Oc"))
+
+
+def test_launch_shape_keeps_every_block_resident(lib):
+    """The library gives an economy several warps only while every block of the launch is resident at once: the
+    8-warp kernel holds 3 blocks per SM (registers), the 4-warp kernel 7; beyond that the one-warp kernel."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    lib.cats_debug_set_warps(0); lib.cats_debug_set_pipe(-1)
+    for B, want in ((1, 8), (3 * sms, 8), (3 * sms + 1, 4), (7 * sms, 4), (7 * sms + 1, 1), (16384, 1)):
+        env = _env(B)
+        shape = env.launch_shape()
+        assert shape["warps_per_economy"] == want, (B, shape)
+        if want > 1:
+            assert shape["goods_market"] == "pipelined"
+        del env

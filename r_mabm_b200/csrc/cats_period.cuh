@@ -604,7 +604,7 @@ __device__ __forceinline__ void job_match(C &c, const unsigned short *seekers, i
                     if (k < z && pick < 0 && c.vac()[cand[k]] > 0) pick = cand[k];
             }
             const bool has = mine && pick >= 0;
-            const unsigned peers = __match_any_sync(FULL, has ? pick : -1 - lane);
+            const unsigned peers = __match_any_sync(FULL, has ? pick : -1);   // (one dummy value: see the goods market)
             const bool ok = !has || __popc(peers & lt) < c.vac()[pick];
             const unsigned badm = __ballot_sync(FULL, mine && !ok);
             const unsigned commit = badm ? (pending & ((1u << (__ffs(badm) - 1)) - 1u)) : pending;
@@ -1158,7 +1158,9 @@ __device__ __forceinline__ void goods_commit_chunk(C &c, Mkt &mkt, unsigned long
             // ---- lanes at the same seller replay the lower lanes' purchases, in lane order
             const bool mine = (pend >> lane) & 1u;
             const bool has = mine && term >= 0;
-            const unsigned peers = __match_any_sync(FULL, has ? term : -1 - lane);
+            // lanes without a terminal share ONE dummy value (they never read their mask): MATCH.ANY takes as long as
+            // there are distinct values in the warp, and from a chunk's second round on most lanes have no terminal
+            const unsigned peers = __match_any_sync(FULL, has ? term : -1);
             unsigned rem = has ? (peers & lt) : 0u;
             double ys = 0.0;
             if (has) ys = mkt.yr[term].x;

@@ -24,8 +24,9 @@ the others (config 2, config 5, config 3 on 8 GPUs) get a 256 MB buffer written 
 per-step event pairs.  `config.l2_policy` says which.
 
 One JSON line on stdout (rank 0).  `value` = device-resident inputs, CUDA events per step, max over ranks;
-`e2e` = the same step through the public API with HOST buffers (pinned upload of actions / mask, download of
-obs / reward / terminated / status / stats inside the timed region).
+`e2e` = the same step through the public API with HOST buffers inside the timed region: the actions / mask uploaded
+from pinned memory with one copy, obs / reward / terminated / status / stats delivered into pinned host memory (the
+kernel writes them in place over PCIe, `cats_step_host`; `--e2e-staged`: explicit copies both ways), one stream sync.
 """
 from __future__ import annotations
 
